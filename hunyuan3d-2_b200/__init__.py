@@ -6,6 +6,13 @@ backed by hand-written CUDA kernels behind the C-ABI declared in
 ``include/hy3dgeo.h``.  There is no CPU fallback: every compute entry point
 raises if ``libhy3dgeo.so`` is missing.
 """
-from . import weights  # noqa: F401
+from . import weights, utils, _lib, volume_decoders, surface_extractors, model  # noqa: F401
+from .model import B200ShapeVAE, GeoDecoder, install, enable_flashvdm_decoder  # noqa: F401
+from .surface_extractors import (DMCSurfaceExtractor, Latent2MeshOutput, MCSurfaceExtractor,  # noqa: F401
+                                 SurfaceExtractor, SurfaceExtractors)
+from .volume_decoders import (FlashVDMVolumeDecoding, HierarchicalVolumeDecoding,  # noqa: F401
+                              VanillaVolumeDecoder)
 
-__all__ = ["weights"]
+__all__ = ["B200ShapeVAE", "GeoDecoder", "install", "enable_flashvdm_decoder", "VanillaVolumeDecoder",
+           "HierarchicalVolumeDecoding", "FlashVDMVolumeDecoding", "MCSurfaceExtractor", "DMCSurfaceExtractor",
+           "SurfaceExtractor", "SurfaceExtractors", "Latent2MeshOutput"]

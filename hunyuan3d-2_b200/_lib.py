@@ -1,0 +1,299 @@
+"""ctypes binding of ``libhy3dgeo.so`` (C-ABI in ``include/hy3dgeo.h``).
+
+There is no fallback: if the shared library is missing or cannot be loaded, any
+attempt to compute raises ``RuntimeError`` (build it with
+``python -c "import __graft_entry__ as g; g.build()"`` or ``make -C hunyuan3d-2_b200/csrc``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+from typing import Optional
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhy3dgeo.so")
+
+PRECISION_FP32_SIMT = 0
+PRECISION_FP16_TC = 1
+
+_lib = None
+_lib_lock = threading.Lock()
+
+c_f32p = C.c_void_p
+c_i32p = C.c_void_p
+
+
+class DecoderDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in
+                ("width", "heads", "mlp_ratio", "latent_width", "num_freqs", "include_pi", "ln_post", "qk_norm")] + \
+               [(n, C.c_void_p) for n in
+                ("query_proj_w", "query_proj_b", "latents_proj_w", "latents_proj_b",
+                 "ln1_w", "ln1_b", "ln2_w", "ln2_b", "ln3_w", "ln3_b",
+                 "c_q_w", "c_q_b", "c_kv_w", "c_kv_b", "c_proj_w", "c_proj_b",
+                 "q_norm_w", "q_norm_b", "k_norm_w", "k_norm_b",
+                 "c_fc_w", "c_fc_b", "mlp_proj_w", "mlp_proj_b",
+                 "ln_post_w", "ln_post_b", "out_w", "out_b")]
+
+
+# name -> (restype, argtypes): every symbol declared in include/hy3dgeo.h
+SYMBOLS = {
+    "hy3d_create": (C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "hy3d_destroy": (None, [C.c_void_p]),
+    "hy3d_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "hy3d_last_error": (C.c_char_p, [C.c_void_p]),
+    "hy3d_set_precision": (C.c_int, [C.c_void_p, C.c_int]),
+    "hy3d_launch_count": (C.c_int64, [C.c_void_p]),
+    "hy3d_set_decoder_weights": (C.c_int, [C.c_void_p, C.POINTER(DecoderDesc)]),
+    "hy3d_prepare_kv": (C.c_int, [C.c_void_p, c_f32p, C.c_int32]),
+    "hy3d_decode_points": (C.c_int, [C.c_void_p, c_f32p, C.c_int64, c_f32p]),
+    "hy3d_decode_dense": (C.c_int, [C.c_void_p, c_f32p, c_f32p, c_f32p, C.c_int32, C.c_int32, C.c_int32,
+                                    C.c_int64, C.c_int64, c_f32p]),
+    "hy3d_decode_list": (C.c_int, [C.c_void_p, c_i32p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                   C.POINTER(C.c_float), C.POINTER(C.c_float), c_f32p]),
+    "hy3d_refine_level": (C.c_int, [C.c_void_p, c_f32p, C.c_int32, C.c_float, C.c_int32, c_i32p, C.c_int64,
+                                    C.POINTER(C.c_int64)]),
+    "hy3d_fill": (C.c_int, [C.c_void_p, c_f32p, C.c_int64, C.c_float]),
+    "hy3d_sentinel_to_nan": (C.c_int, [C.c_void_p, c_f32p, C.c_int64, C.c_float]),
+    "hy3d_mc_count": (C.c_int, [C.c_void_p, c_f32p, C.c_int32, C.c_int32, C.c_int32, C.c_float,
+                                C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_float)]),
+    "hy3d_mc_emit": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                               c_f32p, c_i32p]),
+    "hy3d_debug_watchdog": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
+    "hy3d_debug_retain": (C.c_int, [C.c_void_p, C.c_int]),
+    "hy3d_debug_fetch": (C.c_int, [C.c_void_p, C.c_int, c_f32p, C.c_int64, C.POINTER(C.c_int32)]),
+    "hy3d_mc_cases": (C.c_int, [C.c_void_p, c_f32p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p]),
+}
+
+
+def load_library():
+    """dlopen libhy3dgeo.so and type every exported symbol.  Loud on failure."""
+    global _lib
+    with _lib_lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError(
+                    f"{LIB_PATH} not found: the CUDA extension is not built and there is no fallback. "
+                    "Run `python -c 'import __graft_entry__ as g; g.build()'`.")
+            lib = C.CDLL(LIB_PATH)
+            for name, (res, args) in SYMBOLS.items():
+                fn = getattr(lib, name)          # AttributeError if the .so lacks a declared symbol
+                fn.restype = res
+                fn.argtypes = args
+            _lib = lib
+    return _lib
+
+
+class Hy3dError(RuntimeError):
+    pass
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class GeoContext:
+    """One ``hy3d_ctx`` for one CUDA device.  Not thread-safe (one per thread and
+    device, see ``get_context``).  All launches go to torch's current stream."""
+
+    def __init__(self, device: torch.device):
+        if device.type != "cuda":
+            raise RuntimeError("hy3dgeo runs on CUDA devices only (no CPU fallback)")
+        self.lib = load_library()
+        self.device = torch.device("cuda", device.index if device.index is not None else torch.cuda.current_device())
+        h = C.c_void_p()
+        rc = self.lib.hy3d_create(self.device.index, self._stream(), C.byref(h))
+        if rc != 0:
+            raise Hy3dError(f"hy3d_create failed ({rc}): needs an sm_100 (B200) device")
+        self.h = h
+        self._weights_key = None
+        self._kv_key = None
+        self._keep = []        # tensors that must outlive async copies
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            msg = self.lib.hy3d_last_error(self.h)
+            raise Hy3dError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+    def sync_stream(self):
+        self._check(self.lib.hy3d_set_stream(self.h, self._stream()), "hy3d_set_stream")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.hy3d_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- decoder -----------------------------------------------------------------------------
+    def set_precision(self, precision: int):
+        self._check(self.lib.hy3d_set_precision(self.h, precision), "hy3d_set_precision")
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.hy3d_launch_count(self.h))
+
+    def set_decoder(self, sd, cfg, key=None):
+        """sd: decoder state dict (keys without ``geo_decoder.``), cfg: ShapeVAEConfig."""
+        if key is not None and key == self._weights_key:
+            return
+        self.sync_stream()
+        dev = self.device
+
+        def g(name):
+            t = sd.get(name)
+            if t is None:
+                return None
+            t = t.detach().to(device=dev, dtype=torch.float32).contiguous()
+            self._keep.append(t)
+            return t
+        self._keep = []
+        c = "cross_attn_decoder."
+        d = DecoderDesc()
+        d.width, d.heads = cfg.dec_width, cfg.dec_heads
+        d.mlp_ratio, d.latent_width = cfg.geo_decoder_mlp_expand_ratio, cfg.width
+        d.num_freqs, d.include_pi = cfg.num_freqs, int(cfg.include_pi)
+        d.ln_post, d.qk_norm = int(cfg.geo_decoder_ln_post), int(cfg.dec_qk_norm)
+        names = {
+            "query_proj_w": "query_proj.weight", "query_proj_b": "query_proj.bias",
+            "latents_proj_w": "latents_proj.weight", "latents_proj_b": "latents_proj.bias",
+            "ln1_w": c + "ln_1.weight", "ln1_b": c + "ln_1.bias", "ln2_w": c + "ln_2.weight", "ln2_b": c + "ln_2.bias",
+            "ln3_w": c + "ln_3.weight", "ln3_b": c + "ln_3.bias",
+            "c_q_w": c + "attn.c_q.weight", "c_q_b": c + "attn.c_q.bias",
+            "c_kv_w": c + "attn.c_kv.weight", "c_kv_b": c + "attn.c_kv.bias",
+            "c_proj_w": c + "attn.c_proj.weight", "c_proj_b": c + "attn.c_proj.bias",
+            "q_norm_w": c + "attn.attention.q_norm.weight", "q_norm_b": c + "attn.attention.q_norm.bias",
+            "k_norm_w": c + "attn.attention.k_norm.weight", "k_norm_b": c + "attn.attention.k_norm.bias",
+            "c_fc_w": c + "mlp.c_fc.weight", "c_fc_b": c + "mlp.c_fc.bias",
+            "mlp_proj_w": c + "mlp.c_proj.weight", "mlp_proj_b": c + "mlp.c_proj.bias",
+            "ln_post_w": "ln_post.weight", "ln_post_b": "ln_post.bias",
+            "out_w": "output_proj.weight", "out_b": "output_proj.bias",
+        }
+        for field, name in names.items():
+            t = g(name)
+            setattr(d, field, None if t is None else t.data_ptr())
+        self._check(self.lib.hy3d_set_decoder_weights(self.h, C.byref(d)), "hy3d_set_decoder_weights")
+        torch.cuda.current_stream(self.device).synchronize()     # device->device copies done; staging may go
+        self._keep = []
+        self._weights_key = key
+        self._kv_key = None
+
+    def prepare_kv(self, latents: torch.Tensor):
+        """latents: [M, latent_width] on this device (any float dtype)."""
+        self.sync_stream()
+        lat = latents.detach().to(device=self.device, dtype=torch.float32).contiguous()
+        self._check(self.lib.hy3d_prepare_kv(self.h, _ptr(lat), lat.shape[0]), "hy3d_prepare_kv")
+        self._lat_keep = lat
+
+    def decode_points(self, xyz: torch.Tensor) -> torch.Tensor:
+        self.sync_stream()
+        xyz = xyz.detach().to(device=self.device, dtype=torch.float32).contiguous().view(-1, 3)
+        out = torch.empty(xyz.shape[0], dtype=torch.float32, device=self.device)
+        self._check(self.lib.hy3d_decode_points(self.h, _ptr(xyz), xyz.shape[0], _ptr(out)), "hy3d_decode_points")
+        return out
+
+    def decode_dense(self, axes, first: int, count: int, out: torch.Tensor):
+        """axes: three float32 numpy tables; out: float32 cuda tensor with >= count elements."""
+        self.sync_stream()
+        a = [np.ascontiguousarray(x, dtype=np.float32) for x in axes]
+        self._check(self.lib.hy3d_decode_dense(self.h, a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data,
+                                               len(a[0]), len(a[1]), len(a[2]), first, count, _ptr(out)),
+                    "hy3d_decode_dense")
+
+    def decode_list(self, index: torch.Tensor, n: int, dims, cell, bmin, grid: torch.Tensor):
+        self.sync_stream()
+        cc = (C.c_float * 3)(*[float(v) for v in cell])
+        bb = (C.c_float * 3)(*[float(v) for v in bmin])
+        self._check(self.lib.hy3d_decode_list(self.h, _ptr(index), n, dims[0], dims[1], dims[2], cc, bb, _ptr(grid)),
+                    "hy3d_decode_list")
+
+    def watchdog(self):
+        """Sync and return the tensor-path watchdog record (all zeros = healthy)."""
+        out = (C.c_int32 * 8)()
+        self._check(self.lib.hy3d_debug_watchdog(self.h, out), "hy3d_debug_watchdog")
+        return list(out)
+
+    def debug_retain(self, enable: bool):
+        self._check(self.lib.hy3d_debug_retain(self.h, int(enable)), "hy3d_debug_retain")
+
+    def debug_fetch(self, stage: int, rows: int, max_width: int = 8192) -> torch.Tensor:
+        self.sync_stream()
+        out = torch.empty(rows * max_width, dtype=torch.float32, device=self.device)
+        w = C.c_int32()
+        self._check(self.lib.hy3d_debug_fetch(self.h, stage, _ptr(out), rows, C.byref(w)), "hy3d_debug_fetch")
+        return out[: rows * w.value].view(rows, w.value)
+
+    def check_watchdog(self):
+        rec = self.watchdog()
+        if rec[0]:
+            raise Hy3dError(f"tcgen05 kernel barrier timeout: block {rec[1]} thread {rec[2]} bar 0x{rec[3]:x} parity {rec[4]}")
+
+    # ---- octree -------------------------------------------------------------------------------
+    def refine_level(self, coarse: torch.Tensor, mc_level: float, last: bool, index: Optional[torch.Tensor]) -> int:
+        self.sync_stream()
+        n = coarse.shape[0]
+        cnt = C.c_int64()
+        cap = 0 if index is None else index.numel()
+        self._check(self.lib.hy3d_refine_level(self.h, _ptr(coarse), n, float(mc_level), int(last), _ptr(index), cap,
+                                               C.byref(cnt)), "hy3d_refine_level")
+        return cnt.value
+
+    def fill(self, grid: torch.Tensor, value: float):
+        self.sync_stream()
+        self._check(self.lib.hy3d_fill(self.h, _ptr(grid), grid.numel(), float(value)), "hy3d_fill")
+
+    def sentinel_to_nan(self, grid: torch.Tensor, sentinel: float = -10000.0):
+        self.sync_stream()
+        self._check(self.lib.hy3d_sentinel_to_nan(self.h, _ptr(grid), grid.numel(), float(sentinel)),
+                    "hy3d_sentinel_to_nan")
+
+    # ---- marching cubes ------------------------------------------------------------------------
+    def mc_count(self, grid: torch.Tensor, level: float):
+        self.sync_stream()
+        nv, nf = C.c_int64(), C.c_int64()
+        mm = (C.c_float * 3)()
+        self._check(self.lib.hy3d_mc_count(self.h, _ptr(grid), grid.shape[0], grid.shape[1], grid.shape[2], float(level),
+                                           C.byref(nv), C.byref(nf), mm), "hy3d_mc_count")
+        return nv.value, nf.value, (mm[0], mm[1], bool(mm[2]))
+
+    def mc_emit(self, div, mul, add, verts: torch.Tensor, faces: torch.Tensor):
+        self.sync_stream()
+        d = (C.c_double * 3)(*[float(v) for v in div])
+        m = (C.c_double * 3)(*[float(v) for v in mul])
+        a = (C.c_double * 3)(*[float(v) for v in add])
+        self._check(self.lib.hy3d_mc_emit(self.h, d, m, a, _ptr(verts), _ptr(faces)), "hy3d_mc_emit")
+
+    def mc_cases(self, grid: torch.Tensor, level: float) -> torch.Tensor:
+        self.sync_stream()
+        out = torch.empty(tuple(s - 1 for s in grid.shape), dtype=torch.uint8, device=self.device)
+        self._check(self.lib.hy3d_mc_cases(self.h, _ptr(grid), grid.shape[0], grid.shape[1], grid.shape[2], float(level),
+                                           _ptr(out)), "hy3d_mc_cases")
+        return out
+
+
+_tls = threading.local()
+
+
+def get_context(device) -> GeoContext:
+    """Per-(thread, device) context: per-call state never lives on shared objects
+    (the reference's processors race under api_server threads)."""
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("hy3dgeo runs on CUDA devices only (no CPU fallback)")
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    cache = getattr(_tls, "ctx", None)
+    if cache is None:
+        cache = _tls.ctx = {}
+    if idx not in cache:
+        cache[idx] = GeoContext(torch.device("cuda", idx))
+    return cache[idx]

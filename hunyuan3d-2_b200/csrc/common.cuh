@@ -1,0 +1,143 @@
+// Shared declarations of libhy3dgeo.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/hy3dgeo.h"
+
+#define HY3D_SENTINEL (-10000.0f)
+#define HY3D_BAND 0.95f
+
+struct DevBuf {                       // grow-only device scratch
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// Decoder weights kept on the device.  fp32 copies feed the SIMT path and the per-latent K/V
+// projection; fp16 UMMA-tiled copies feed the tcgen05 path (built in decoder_tc.cu).
+struct DecoderWeights {
+  bool set = false;
+  int W = 0, H = 0, D = 0, R = 0, LW = 0, F = 0, E = 0;   // width, heads, head dim, mlp ratio, latent width, freqs, embed dim
+  bool include_pi = false, ln_post = true, qk_norm = true;
+  bool has_latents_proj = false, has_cq_b = false, has_ckv_b = false;
+  float freqs[16];
+  DevBuf f32;                         // one slab holding all fp32 tensors
+  const float *qp_w, *qp_b, *lp_w, *lp_b, *ln1_w, *ln1_b, *ln2_w, *ln2_b, *ln3_w, *ln3_b;
+  const float *cq_w, *cq_b, *ckv_w, *ckv_b, *cproj_w, *cproj_b, *qn_w, *qn_b, *kn_w, *kn_b;
+  const float *fc_w, *fc_b, *mp_w, *mp_b, *lnp_w, *lnp_b, *out_w, *out_b;
+  // tcgen05 operand images (decoder_tc.cu)
+  DevBuf tc;
+  const __half *t_qp, *t_cq, *t_cproj, *t_fc, *t_mp;      // B tiles
+};
+
+struct KVState {
+  bool ready = false;
+  int M = 0;                          // tokens
+  int Mpad = 0;                       // tokens padded to 128
+  DevBuf k32, v32;                    // fp32 [H, M, D] (after k_norm) — SIMT path + selection
+  DevBuf ktile, vtile;                // fp16 UMMA tiles — tcgen05 path
+};
+
+struct McState {
+  bool counted = false;
+  const float* grid = nullptr;
+  int n0 = 0, n1 = 0, n2 = 0, words = 0;
+  float level = 0.f;
+  long long nV = 0, nF = 0;
+  DevBuf bits, rowcnt, rowoff, stats;
+};
+
+struct hy3d_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int precision = HY3D_PRECISION_FP16_TC;
+  int num_sms = 148;
+  long long launches = 0;
+  std::string err;
+  DecoderWeights w;
+  KVState kv;
+  McState mc;
+  DevBuf ws[12];                      // decoder workspaces
+  DevBuf scratch, scratch2;           // octree / misc
+  void* pinned = nullptr;             // small pinned host buffer for read-backs
+  // diagnostics: per-stage activations of the last decoded chunk (hy3d_debug_retain / hy3d_debug_fetch)
+  int debug_retain = 0;
+  DevBuf dbg[8];
+  int dbg_layout[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // 0 row-major fp32, 1 R32, 2 T16
+  long long dbg_rows = 0;
+  int dbg_width[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+// stage ids: 0 x0, 1 ln_1(x0), 2 q (after q_norm), 3 attention out, 4 x1, 5 ln_3(x1), 6 mlp hidden, 7 x2
+int hy3d_debug_keep(hy3d_ctx* ctx, int stage, const void* src, size_t bytes, int layout, long long rows, int width);
+
+int hy3d_fail(hy3d_ctx* ctx, int code, const char* fmt, ...);
+
+#define HY3D_CUDA(ctx, expr)                                                                   \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess)                                                                     \
+      return hy3d_fail(ctx, HY3D_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr,        \
+                       cudaGetErrorString(_e));                                                \
+  } while (0)
+
+#define HY3D_LAUNCH_CHECK(ctx)                                                                 \
+  do {                                                                                         \
+    (ctx)->launches++;                                                                         \
+    HY3D_CUDA(ctx, cudaGetLastError());                                                        \
+  } while (0)
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- decoder entry points implemented per precision --------------------------------------
+struct QuerySource {
+  int mode;                 // 0 explicit xyz, 1 dense grid range, 2 index list
+  const float* xyz;         // mode 0
+  const float* axis;        // mode 1: device table [n0 + n1 + n2]
+  const int32_t* index;     // mode 2
+  int n0, n1, n2;
+  long long first;          // mode 1
+  float cell[3], bmin[3];   // mode 2
+};
+// out_mode 0: out[q] = logit ; 1: out[index[q]] = logit (skip index < 0)
+int hy3d_decode_simt(hy3d_ctx* ctx, const QuerySource& src, long long n, float* d_out, int out_mode);
+int hy3d_decode_tc(hy3d_ctx* ctx, const QuerySource& src, long long n, float* d_out, int out_mode);
+int hy3d_tc_prepare_weights(hy3d_ctx* ctx);
+int hy3d_tc_prepare_kv(hy3d_ctx* ctx);
+int hy3d_simt_prepare_kv(hy3d_ctx* ctx, const float* d_latents, int M);
+
+__device__ __forceinline__ void hy3d_query_point(const QuerySource& s, long long q, float& x, float& y, float& z,
+                                                 long long& out_idx) {
+  if (s.mode == 0) {
+    x = s.xyz[3 * q]; y = s.xyz[3 * q + 1]; z = s.xyz[3 * q + 2]; out_idx = q;
+  } else if (s.mode == 1) {
+    long long lin = s.first + q;
+    int k = (int)(lin % s.n2); long long t = lin / s.n2;
+    int j = (int)(t % s.n1); int i = (int)(t / s.n1);
+    x = s.axis[i]; y = s.axis[s.n0 + j]; z = s.axis[s.n0 + s.n1 + k]; out_idx = q;
+  } else {
+    int lin = s.index[q];
+    out_idx = lin;
+    if (lin < 0) { x = y = z = 0.f; return; }
+    int k = lin % s.n2; int t = lin / s.n2;
+    int j = t % s.n1; int i = t / s.n1;
+    // volume_decoders.py:394-396: float32(idx) * float32(cell) + float32(bbox_min), no FMA contraction
+    x = __fadd_rn(__fmul_rn((float)i, s.cell[0]), s.bmin[0]);
+    y = __fadd_rn(__fmul_rn((float)j, s.cell[1]), s.bmin[1]);
+    z = __fadd_rn(__fmul_rn((float)k, s.cell[2]), s.bmin[2]);
+  }
+}

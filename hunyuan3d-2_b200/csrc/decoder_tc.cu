@@ -1,0 +1,751 @@
+// tcgen05 / TMEM decoder (HY3D_PRECISION_FP16_TC): CrossAttentionDecoder.forward (reference
+// attention_blocks.py:483-493) for batches of query points, fp16 operands with
+// fp32 accumulation in tensor memory.
+//
+// Memory layout (all chosen so that every operand tile is ONE contiguous 16/32 KB block that a
+// single 1-D bulk async copy (cp.async.bulk, SASS UBLKCP) drops into shared memory already in the
+// 128-byte-swizzled K-major form the UMMA descriptors expect — no tensor maps, no strided TMA):
+//   "T16"  fp16 activations  [P/128][K/64][128 rows x 64 cols, SW128]        (16 KB tiles)
+//   "B16"  fp16 weights      [N/256][K/64][256 rows x 64 cols, SW128]        (32 KB tiles)
+//   "R32"  fp32 residual     [P/128][N/4][128 rows][4]   (row-per-thread epilogues read/write 512 B
+//                                                          contiguous per warp instruction)
+//   K      fp16 [group][head][M/128][128 tok x 64, SW128]      V^T fp16 [group][head][M/128][2][64 d x 64 tok, SW128]
+//
+// Stage chain per chunk of points (one launch each, activations through HBM/L2; the chain is
+// compute-bound: ~30 KB/point of traffic vs 33.7 MFLOP/point):
+//   k_embed_tc      Fourier features, fp16 hi/lo split          -> T16 [.,3]
+//   k_gemm_tc<X0>   query_proj (3-term split fp16 = ~fp32)      -> R32 x0
+//   k_ln_tc         ln_1                                         -> T16
+//   k_gemm_tc<Q>    c_q, per-head q_norm, *scale*log2e           -> T16 q (k-block == head)
+//   k_attn_tc       softmax(q k^T) v, online softmax, 2 heads in flight per CTA -> T16
+//   k_gemm_tc<RES>  c_proj + residual                            -> R32 x1
+//   k_ln_tc         ln_3                                         -> T16
+//   k_gemm_tc<GELU> c_fc + erf-GELU                              -> T16 h
+//   k_gemm_tc<RES>  mlp.c_proj + residual                        -> R32 x2
+//   k_head_tc       [ln_post] + output_proj                      -> logits (dense or scattered)
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+using namespace tc;
+
+namespace {
+
+constexpr int TILE_M = 128;
+constexpr int TILE_BYTES = 16384;          // 128 x 64 fp16
+constexpr int BN = 256;                    // GEMM N tile
+constexpr int BTILE_BYTES = BN * 128;      // 256 x 64 fp16
+constexpr int GEMM_STAGES = 4;
+constexpr int GEMM_THREADS = 384;          // warp0 producer, warp1 mma, warp2 tmem, warp3 idle, warps 4..11 epilogue
+constexpr float LOG2E = 1.4426950408889634f;
+
+enum { EPI_X0 = 0, EPI_Q = 1, EPI_RES = 2, EPI_GELU = 3 };
+
+struct GemmTC {
+  const uint8_t* A;      // T16 tiles [Mb][KB]
+  const uint8_t* B;      // B16 tiles [Nb][KB]
+  int Mb, Nb, KB, N;
+  const float* bias;     // [N] or null
+  const float* Rin;      // R32 (EPI_RES)
+  float* Rout;           // R32 (EPI_X0, EPI_RES)
+  uint8_t* Tout;         // T16 (EPI_Q, EPI_GELU)
+  const float* qn_w; const float* qn_b; int qk_norm; float qscale;   // EPI_Q
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+
+__device__ __forceinline__ void store_t16_chunk(uint8_t* tile, int r, int c16, const float* v) {
+  uint4 u;
+  u.x = pack_h2(v[0], v[1]); u.y = pack_h2(v[2], v[3]); u.z = pack_h2(v[4], v[5]); u.w = pack_h2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(tile + sw128_off(r, c16)) = u;
+}
+
+// ------------------------------------------------------------------------------------------
+// Persistent warp-specialised GEMM:  C[P, N] = A[P, K] * W[N, K]^T with a fused epilogue.
+// ------------------------------------------------------------------------------------------
+template <int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(GemmTC g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;                                      // [STAGES][16 KB]
+  uint8_t* sB = smem + GEMM_STAGES * TILE_BYTES;           // [STAGES][32 KB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GEMM_STAGES * (TILE_BYTES + BTILE_BYTES));
+  // bars: full[S], empty[S], tfull[2], tempty[2]
+  const uint32_t bar0 = smem_u32(bars);
+  auto FULL = [&](int s) { return bar0 + 8u * s; };
+  auto EMPTY = [&](int s) { return bar0 + 8u * (GEMM_STAGES + s); };
+  auto TFULL = [&](int a) { return bar0 + 8u * (2 * GEMM_STAGES + a); };
+  auto TEMPTY = [&](int a) { return bar0 + 8u * (2 * GEMM_STAGES + 2 + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * GEMM_STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < GEMM_STAGES; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(TFULL(a), 1); mbar_init(TEMPTY(a), 8); }
+    fence_barrier_init();
+  }
+  if (warp == 2) { tmem_alloc(smem_u32(tmem_slot), 512); tmem_relinquish(); }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  const int ntiles = g.Mb * g.Nb;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int mb = t / g.Nb, nb = t % g.Nb;
+        const uint8_t* a = g.A + (size_t)mb * g.KB * TILE_BYTES;
+        const uint8_t* b = g.B + (size_t)nb * g.KB * BTILE_BYTES;
+        for (int kb = 0; kb < g.KB; ++kb) {
+          mbar_wait(EMPTY(s), ph ^ 1);
+          mbar_arrive_expect_tx(FULL(s), TILE_BYTES + BTILE_BYTES);
+          bulk_g2s(smem_u32(sA + s * TILE_BYTES), a + (size_t)kb * TILE_BYTES, TILE_BYTES, FULL(s));
+          bulk_g2s(smem_u32(sB + s * BTILE_BYTES), b + (size_t)kb * BTILE_BYTES, BTILE_BYTES, FULL(s));
+          if (++s == GEMM_STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(TILE_M, BN);
+      int s = 0; uint32_t ph = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t aph = (it >> 1) & 1;
+        mbar_wait(TEMPTY(acc), aph ^ 1);
+        fence_after_sync();
+        const uint32_t d = tmem + acc * BN;
+        for (int kb = 0; kb < g.KB; ++kb) {
+          mbar_wait(FULL(s), ph);
+          fence_after_sync();
+          const uint64_t ad = make_desc_sw128(smem_u32(sA + s * TILE_BYTES));
+          const uint64_t bd = make_desc_sw128(smem_u32(sB + s * BTILE_BYTES));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) mma_f16_ss(d, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
+          mma_commit(EMPTY(s));
+          if (++s == GEMM_STAGES) { s = 0; ph ^= 1; }
+        }
+        mma_commit(TFULL(acc));
+      }
+    }
+  } else if (warp >= 4) {
+    const int e = warp - 4;
+    const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int half = e >> 2;                // column half of the 256-wide tile
+    const int r = q * 32 + lane;            // row inside the tile
+    int it = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+      const int mb = t / g.Nb, nb = t % g.Nb;
+      const int acc = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      mbar_wait(TFULL(acc), aph);
+      fence_after_sync();
+      const uint32_t trow = tmem + acc * BN + ((uint32_t)(q * 32) << 16);
+      const int col0 = nb * BN + half * (BN / 2);          // first global column of this warp's half
+      if constexpr (EPI == EPI_Q) {
+#pragma unroll 1
+        for (int hh = 0; hh < 2; ++hh) {                    // two 64-column heads per half
+          uint32_t v[64];
+          HY3D_TMEM_LD32(trow + half * (BN / 2) + hh * 64, v);
+          HY3D_TMEM_LD32(trow + half * (BN / 2) + hh * 64 + 32, (v + 32));
+          tmem_wait_ld();
+          const int c = col0 + hh * 64;
+          float x[64];
+#pragma unroll
+          for (int i = 0; i < 64; ++i) x[i] = __uint_as_float(v[i]) + (g.bias ? __ldg(g.bias + c + i) : 0.f);
+          if (g.qk_norm) {
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < 64; ++i) s += x[i];
+            const float mean = s * (1.f / 64.f);
+            float var = 0.f;
+#pragma unroll
+            for (int i = 0; i < 64; ++i) { float d = x[i] - mean; var += d * d; }
+            const float rstd = rsqrtf(var * (1.f / 64.f) + 1e-6f);
+#pragma unroll
+            for (int i = 0; i < 64; ++i) x[i] = ((x[i] - mean) * rstd * __ldg(g.qn_w + i) + __ldg(g.qn_b + i)) * g.qscale;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 64; ++i) x[i] *= g.qscale;
+          }
+          uint8_t* tile = g.Tout + ((size_t)mb * (g.N / 64) + (c >> 6)) * TILE_BYTES;
+#pragma unroll
+          for (int c16 = 0; c16 < 8; ++c16) store_t16_chunk(tile, r, c16, x + 8 * c16);
+        }
+      } else {
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {                    // four 32-column chunks per half
+          uint32_t v[32];
+          HY3D_TMEM_LD32(trow + half * (BN / 2) + ch * 32, v);
+          tmem_wait_ld();
+          const int c = col0 + ch * 32;
+          float x[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(v[i]) + (g.bias ? __ldg(g.bias + c + i) : 0.f);
+          if constexpr (EPI == EPI_GELU) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) x[i] = gelu_erf(x[i]);
+            uint8_t* tile = g.Tout + ((size_t)mb * (g.N / 64) + (c >> 6)) * TILE_BYTES;
+            const int cbase = (c & 63) >> 3;
+#pragma unroll
+            for (int c16 = 0; c16 < 4; ++c16) store_t16_chunk(tile, r, cbase + c16, x + 8 * c16);
+          } else {
+            // R32: [mb][c/4][row][4]
+            const size_t base = ((size_t)mb * (g.N / 4) + (c >> 2)) * TILE_M + r;
+#pragma unroll
+            for (int i4 = 0; i4 < 8; ++i4) {
+              float4 o = make_float4(x[4 * i4], x[4 * i4 + 1], x[4 * i4 + 2], x[4 * i4 + 3]);
+              const size_t idx = base + (size_t)i4 * TILE_M;
+              if constexpr (EPI == EPI_RES) {
+                const float4 rr = __ldg(reinterpret_cast<const float4*>(g.Rin) + idx);
+                o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+              }
+              reinterpret_cast<float4*>(g.Rout)[idx] = o;
+            }
+          }
+        }
+      }
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(TEMPTY(acc));
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+constexpr size_t GEMM_SMEM = 1024 + GEMM_STAGES * (TILE_BYTES + BTILE_BYTES) + 256;
+
+// ------------------------------------------------------------------------------------------
+// Attention: per CTA one 128-query tile, two heads in flight (softmax warpgroup per head).
+// ------------------------------------------------------------------------------------------
+constexpr int ATT_THREADS = 384;           // warp0 producer, warp1 mma, warp2 tmem, warp3 idle, WG1 head a, WG2 head b
+constexpr int ATT_SLOTS = 6;               // K / V^T ring, 16 KB each
+constexpr int TM_S0 = 0, TM_O0 = 256;      // TMEM columns: S[a] at a*128, O[a] at 256 + a*64
+
+struct AttnTC {
+  const uint8_t* Q;      // T16 [Pb][H]
+  const uint8_t* K;      // [group][H][nkv][16 KB]
+  const uint8_t* V;      // [group][H][nkv][16 KB]
+  uint8_t* O;            // T16 [Pb][H]
+  const int* tile_group; // per q-tile KV group or null
+  const int* group_ntok; // valid tokens per group or null
+  int Pb, H, nkv, ntok;  // nkv = tiles per (group, head); ntok = valid tokens when group_ntok == null
+};
+
+__global__ void __launch_bounds__(ATT_THREADS, 1) k_attn_tc(AttnTC g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                                   // [2][16 KB]
+  uint8_t* sP = smem + 2 * TILE_BYTES;                  // [2][32 KB]
+  uint8_t* sKV = smem + 2 * TILE_BYTES + 2 * 2 * TILE_BYTES;   // [SLOTS][16 KB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + ATT_SLOTS * TILE_BYTES);
+  const uint32_t bar0 = smem_u32(bars);
+  auto KVFULL = [&](int s) { return bar0 + 8u * s; };
+  auto KVEMPTY = [&](int s) { return bar0 + 8u * (ATT_SLOTS + s); };
+  const uint32_t QFULL = bar0 + 8u * (2 * ATT_SLOTS), QEMPTY = QFULL + 8;
+  auto SFULL = [&](int a) { return QEMPTY + 8u + 8u * a; };
+  auto SEMPTY = [&](int a) { return QEMPTY + 8u + 8u * (2 + a); };
+  auto PFULL = [&](int a) { return QEMPTY + 8u + 8u * (4 + a); };
+  auto PVDONE = [&](int a) { return QEMPTY + 8u + 8u * (6 + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * ATT_SLOTS + 2 + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < ATT_SLOTS; ++s) { mbar_init(KVFULL(s), 1); mbar_init(KVEMPTY(s), 1); }
+    mbar_init(QFULL, 1); mbar_init(QEMPTY, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(SFULL(a), 1); mbar_init(SEMPTY(a), 4); mbar_init(PFULL(a), 4); mbar_init(PVDONE(a), 1); }
+    fence_barrier_init();
+  }
+  if (warp == 2) { tmem_alloc(smem_u32(tmem_slot), 512); tmem_relinquish(); }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  const int HP = g.H / 2;
+  const int nitems = g.Pb * HP;
+  const int nkv = g.nkv;
+
+  if (warp < 4) {
+    reg_dealloc<80>();
+    if (warp == 0 && lane == 0) {
+      // ---------------- producer: Q pair, then K0 K1 (j=0), then per j: K0 K1 (j+1), V0 V1 (j) ----------------
+      int s = 0; uint32_t ph = 0; uint32_t qph = 0;
+      auto push = [&](const uint8_t* src) {
+        mbar_wait(KVEMPTY(s), ph ^ 1);
+        mbar_arrive_expect_tx(KVFULL(s), TILE_BYTES);
+        bulk_g2s(smem_u32(sKV + s * TILE_BYTES), src, TILE_BYTES, KVFULL(s));
+        if (++s == ATT_SLOTS) { s = 0; ph ^= 1; }
+      };
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int qt = item / HP, h0 = (item % HP) * 2;
+        const int grp = g.tile_group ? g.tile_group[qt] : 0;
+        mbar_wait(QEMPTY, qph ^ 1);
+        mbar_arrive_expect_tx(QFULL, 2 * TILE_BYTES);
+        bulk_g2s(smem_u32(sQ), g.Q + ((size_t)qt * g.H + h0) * TILE_BYTES, 2 * TILE_BYTES, QFULL);   // heads h0, h0+1 adjacent
+        qph ^= 1;
+        const uint8_t* kb[2]; const uint8_t* vb[2];
+        for (int a = 0; a < 2; ++a) {
+          kb[a] = g.K + ((size_t)grp * g.H + h0 + a) * nkv * TILE_BYTES;
+          vb[a] = g.V + ((size_t)grp * g.H + h0 + a) * nkv * TILE_BYTES;
+        }
+        push(kb[0]); push(kb[1]);
+        for (int j = 0; j < nkv; ++j) {
+          if (j + 1 < nkv) { push(kb[0] + (size_t)(j + 1) * TILE_BYTES); push(kb[1] + (size_t)(j + 1) * TILE_BYTES); }
+          push(vb[0] + (size_t)j * TILE_BYTES); push(vb[1] + (size_t)j * TILE_BYTES);
+        }
+      }
+    } else if (warp == 1 && lane == 0) {
+      // ---------------- MMA issuer ----------------
+      const uint32_t idesc_s = make_idesc_f16(128, 128);
+      const uint32_t idesc_o = make_idesc_f16(128, 64);
+      int s = 0; uint32_t ph = 0; uint32_t qph = 0;
+      uint32_t sph[2] = {0, 0}, pph[2] = {0, 0};      // phases of SEMPTY / PFULL waits
+      auto issue_s = [&](int a) {
+        mbar_wait(KVFULL(s), ph);
+        mbar_wait(SEMPTY(a), sph[a] ^ 1); sph[a] ^= 1;
+        fence_after_sync();
+        const uint64_t ad = make_desc_sw128(smem_u32(sQ + a * TILE_BYTES));
+        const uint64_t bd = make_desc_sw128(smem_u32(sKV + s * TILE_BYTES));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) mma_f16_ss(tmem + TM_S0 + a * 128, ad + 2 * k, bd + 2 * k, idesc_s, k != 0);
+        mma_commit(KVEMPTY(s));
+        mma_commit(SFULL(a));
+        if (++s == ATT_SLOTS) { s = 0; ph ^= 1; }
+      };
+      auto issue_pv = [&](int a, int j) {
+        mbar_wait(KVFULL(s), ph);
+        mbar_wait(PFULL(a), pph[a]); pph[a] ^= 1;
+        fence_after_sync();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint64_t ad = make_desc_sw128(smem_u32(sP + a * 2 * TILE_BYTES + (k >> 2) * TILE_BYTES)) + 2 * (k & 3);
+          const uint64_t bd = make_desc_sw128(smem_u32(sKV + s * TILE_BYTES + (k >> 2) * (TILE_BYTES / 2))) + 2 * (k & 3);
+          mma_f16_ss(tmem + TM_O0 + a * 64, ad, bd, idesc_o, (j | k) != 0);
+        }
+        mma_commit(KVEMPTY(s));
+        mma_commit(PVDONE(a));
+        if (++s == ATT_SLOTS) { s = 0; ph ^= 1; }
+      };
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        mbar_wait(QFULL, qph); qph ^= 1;
+        fence_after_sync();
+        issue_s(0); issue_s(1);
+        for (int j = 0; j < nkv; ++j) {
+          if (j + 1 < nkv) { issue_s(0); issue_s(1); }
+          else mma_commit(QEMPTY);                     // all S MMAs of this item issued: Q may be refilled once they finish
+          issue_pv(0, j); issue_pv(1, j);
+        }
+      }
+    }
+  } else {
+    reg_alloc<200>();
+    // ---------------- softmax warpgroups: a = head slot, one thread per query row ----------------
+    const int a = (warp - 4) >> 2;
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t t_s = tmem + TM_S0 + a * 128 + ((uint32_t)(q * 32) << 16);
+    const uint32_t t_o = tmem + TM_O0 + a * 64 + ((uint32_t)(q * 32) << 16);
+    uint8_t* sPa = sP + a * 2 * TILE_BYTES;
+    uint32_t sfull_ph = 0, pv_ph = 0;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+      const int qt = item / HP, h = (item % HP) * 2 + a;
+      const int ntok = g.group_ntok ? g.group_ntok[g.tile_group ? g.tile_group[qt] : 0] : g.ntok;
+      float m = -INFINITY, l = 0.f;
+      for (int j = 0; j < nkv; ++j) {
+        mbar_wait(SFULL(a), sfull_ph); sfull_ph ^= 1;
+        fence_after_sync();
+        uint32_t sv[128];
+        HY3D_TMEM_LD32(t_s, sv); HY3D_TMEM_LD32(t_s + 32, (sv + 32));
+        HY3D_TMEM_LD32(t_s + 64, (sv + 64)); HY3D_TMEM_LD32(t_s + 96, (sv + 96));
+        tmem_wait_ld();
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(SEMPTY(a));
+        const int valid = ntok - j * 128;              // columns >= valid are padding tokens
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 128; ++i) {
+          float x = __uint_as_float(sv[i]);
+          if (i >= valid) { x = -INFINITY; sv[i] = __float_as_uint(x); }
+          mx = fmaxf(mx, x);
+        }
+        bool need = false;
+        float m_new = m;
+        if (j == 0) { m_new = mx; }
+        else if (mx > m + 8.f) { m_new = mx; need = true; }   // lazy rescale: keep the old max while p <= 2^8
+        if (j > 0) {
+          mbar_wait(PVDONE(a), pv_ph); pv_ph ^= 1;            // P buffer free, O holds tiles < j
+          fence_after_sync();
+          if (__any_sync(0xffffffffu, need)) {
+            const float sc = need ? ex2(m - m_new) : 1.f;
+            l *= sc;
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
+              uint32_t ov[32];
+              HY3D_TMEM_LD32(t_o + c * 32, ov);
+              tmem_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * sc);
+              HY3D_TMEM_ST32(t_o + c * 32, ov);
+            }
+            tmem_wait_st();
+          }
+        }
+        m = m_new;
+        float sum = 0.f;
+#pragma unroll
+        for (int c16 = 0; c16 < 16; ++c16) {
+          float p[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { p[i] = ex2(__uint_as_float(sv[c16 * 8 + i]) - m); sum += p[i]; }
+          store_t16_chunk(sPa + (c16 >> 3) * TILE_BYTES, r, c16 & 7, p);
+        }
+        l += sum;
+        fence_proxy_async_smem();
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(PFULL(a));
+      }
+      // ---- finalize: O / l -> fp16 tile (q-tile, head) ----
+      mbar_wait(PVDONE(a), pv_ph); pv_ph ^= 1;
+      fence_after_sync();
+      const float inv = 1.f / l;
+      uint8_t* tile = g.O + ((size_t)qt * g.H + h) * TILE_BYTES;
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t ov[32];
+        HY3D_TMEM_LD32(t_o + c * 32, ov);
+        tmem_wait_ld();
+        float x[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(ov[i]) * inv;
+#pragma unroll
+        for (int c16 = 0; c16 < 4; ++c16) store_t16_chunk(tile, r, c * 4 + c16, x + 8 * c16);
+      }
+      fence_before_sync();
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+constexpr size_t ATT_SMEM = 1024 + (2 + 4 + ATT_SLOTS) * TILE_BYTES + 512;
+
+// ------------------------------------------------------------------------------------------
+// Small HBM-bound stages around the GEMMs
+// ------------------------------------------------------------------------------------------
+// Fourier embedding (attention_blocks.py:112-130) -> T16 with K = 192: [e_hi | e_lo | e_hi]
+__global__ void __launch_bounds__(128) k_embed_tc(QuerySource src, long long n, int F, float pi_mul, uint8_t* __restrict__ T) {
+  const int r = threadIdx.x;
+  const long long qi = (long long)blockIdx.x * TILE_M + r;
+  float c[3] = {0.f, 0.f, 0.f};
+  long long oi;
+  if (qi < n) hy3d_query_point(src, qi, c[0], c[1], c[2], oi);
+  float e[64];
+#pragma unroll
+  for (int i = 0; i < 64; ++i) e[i] = 0.f;
+  e[0] = c[0]; e[1] = c[1]; e[2] = c[2];
+  for (int a = 0; a < 3; ++a)
+    for (int f = 0; f < F; ++f) {
+      float s, co;
+      sincosf(__fmul_rn(c[a], exp2f((float)f) * pi_mul), &s, &co);
+      e[3 + a * F + f] = s;
+      e[3 + 3 * F + a * F + f] = co;
+    }
+  uint8_t* t0 = T + (size_t)blockIdx.x * 3 * TILE_BYTES;
+#pragma unroll
+  for (int c16 = 0; c16 < 8; ++c16) {
+    float hi[8], lo[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float v = e[c16 * 8 + i];
+      float h = __half2float(__float2half_rn(v));
+      hi[i] = h; lo[i] = v - h;
+    }
+    store_t16_chunk(t0, r, c16, hi);
+    store_t16_chunk(t0 + TILE_BYTES, r, c16, lo);
+    store_t16_chunk(t0 + 2 * TILE_BYTES, r, c16, hi);
+  }
+}
+
+// LayerNorm over N columns: R32 -> T16 (one thread per row, one block per 128-row tile)
+__global__ void __launch_bounds__(128) k_ln_tc(const float* __restrict__ R, int N, const float* __restrict__ gam,
+                                                const float* __restrict__ bet, float eps, uint8_t* __restrict__ T) {
+  const int r = threadIdx.x;
+  const float4* x = reinterpret_cast<const float4*>(R) + (size_t)blockIdx.x * (N / 4) * TILE_M + r;
+  const int n4 = N / 4;
+  const float shift = __ldg(&x[0]).x;
+  float s = 0.f, ss = 0.f;
+#pragma unroll 8
+  for (int c = 0; c < n4; ++c) {
+    float4 v = __ldg(&x[(size_t)c * TILE_M]);
+    float a0 = v.x - shift, a1 = v.y - shift, a2 = v.z - shift, a3 = v.w - shift;
+    s += (a0 + a1) + (a2 + a3);
+    ss += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+  }
+  const float ms = s / N;
+  const float mean = shift + ms;
+  const float var = fmaxf(ss / N - ms * ms, 0.f);
+  const float rstd = rsqrtf(var + eps);
+  uint8_t* tbase = T + (size_t)blockIdx.x * (N / 64) * TILE_BYTES;
+#pragma unroll 4
+  for (int c8 = 0; c8 < N / 8; ++c8) {
+    float4 v0 = __ldg(&x[(size_t)(2 * c8) * TILE_M]), v1 = __ldg(&x[(size_t)(2 * c8 + 1) * TILE_M]);
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gam) + 2 * c8), g1 = __ldg(reinterpret_cast<const float4*>(gam) + 2 * c8 + 1);
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bet) + 2 * c8), b1 = __ldg(reinterpret_cast<const float4*>(bet) + 2 * c8 + 1);
+    float o[8];
+    o[0] = (v0.x - mean) * rstd * g0.x + b0.x; o[1] = (v0.y - mean) * rstd * g0.y + b0.y;
+    o[2] = (v0.z - mean) * rstd * g0.z + b0.z; o[3] = (v0.w - mean) * rstd * g0.w + b0.w;
+    o[4] = (v1.x - mean) * rstd * g1.x + b1.x; o[5] = (v1.y - mean) * rstd * g1.y + b1.y;
+    o[6] = (v1.z - mean) * rstd * g1.z + b1.z; o[7] = (v1.w - mean) * rstd * g1.w + b1.w;
+    store_t16_chunk(tbase + (size_t)(c8 >> 3) * TILE_BYTES, r, c8 & 7, o);
+  }
+}
+
+// [ln_post] + output_proj (attention_blocks.py:490-492): R32 -> logits
+__global__ void __launch_bounds__(128) k_head_tc(const float* __restrict__ R, int N, const float* __restrict__ gam,
+                                                  const float* __restrict__ bet, const float* __restrict__ wout,
+                                                  const float* __restrict__ bout, QuerySource src, long long n,
+                                                  float* __restrict__ out, int out_mode) {
+  const int r = threadIdx.x;
+  const long long qi = (long long)blockIdx.x * TILE_M + r;
+  const float4* x = reinterpret_cast<const float4*>(R) + (size_t)blockIdx.x * (N / 4) * TILE_M + r;
+  const int n4 = N / 4;
+  float dot = 0.f;
+  if (gam) {
+    const float shift = __ldg(&x[0]).x;
+    float s = 0.f, ss = 0.f;
+#pragma unroll 8
+    for (int c = 0; c < n4; ++c) {
+      float4 v = __ldg(&x[(size_t)c * TILE_M]);
+      float a0 = v.x - shift, a1 = v.y - shift, a2 = v.z - shift, a3 = v.w - shift;
+      s += (a0 + a1) + (a2 + a3);
+      ss += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+    }
+    const float ms = s / N, mean = shift + ms;
+    const float rstd = rsqrtf(fmaxf(ss / N - ms * ms, 0.f) + 1e-5f);
+#pragma unroll 8
+    for (int c = 0; c < n4; ++c) {
+      float4 v = __ldg(&x[(size_t)c * TILE_M]);
+      const float4 gg = __ldg(reinterpret_cast<const float4*>(gam) + c), bb = __ldg(reinterpret_cast<const float4*>(bet) + c);
+      const float4 ww = __ldg(reinterpret_cast<const float4*>(wout) + c);
+      dot += ((v.x - mean) * rstd * gg.x + bb.x) * ww.x + ((v.y - mean) * rstd * gg.y + bb.y) * ww.y +
+             ((v.z - mean) * rstd * gg.z + bb.z) * ww.z + ((v.w - mean) * rstd * gg.w + bb.w) * ww.w;
+    }
+  } else {
+#pragma unroll 8
+    for (int c = 0; c < n4; ++c) {
+      float4 v = __ldg(&x[(size_t)c * TILE_M]);
+      const float4 ww = __ldg(reinterpret_cast<const float4*>(wout) + c);
+      dot += v.x * ww.x + v.y * ww.y + v.z * ww.z + v.w * ww.w;
+    }
+  }
+  if (qi >= n) return;
+  long long oi = qi;
+  if (out_mode == 1) { oi = src.index[qi]; if (oi < 0) return; }
+  out[oi] = dot + __ldg(bout);
+}
+
+// ---- operand image builders ----------------------------------------------------------------
+// fp32 row-major W[N, K] (ld = ldw) -> B16 tiles.  mode 0: plain.  mode 1: query_proj split:
+// K_out = 192 = [W_hi | W_hi | W_lo] over the first E columns (zero padded to 64).
+__global__ void k_build_b16(const float* __restrict__ Wsrc, int N, int K, int ldw, int mode, int E, uint8_t* __restrict__ out) {
+  const int KB = K / 64;
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;    // one 16-byte chunk per thread
+  long long total = (long long)N * (K / 8);
+  if (t >= total) return;
+  const int c8 = (int)(t % (K / 8)); const int n = (int)(t / (K / 8));
+  const int kb = c8 >> 3, c16 = c8 & 7;
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int k = c8 * 8 + i;
+    float w;
+    if (mode == 0) w = Wsrc[(size_t)n * ldw + k];
+    else {
+      int part = k / 64, kk = k % 64;
+      float full = kk < E ? Wsrc[(size_t)n * ldw + kk] : 0.f;
+      float hi = __half2float(__float2half_rn(full));
+      w = part < 2 ? hi : full - hi;
+    }
+    v[i] = w;
+  }
+  uint8_t* tile = out + ((size_t)(n / BN) * KB + kb) * BTILE_BYTES;
+  store_t16_chunk(tile, n % BN, c16, v);
+}
+
+// k32 [H, M, 64] -> K tiles; vT32 [H, 64, M] -> V^T tiles (zero padded to Mpad tokens)
+__global__ void k_build_kv(const float* __restrict__ k32, const float* __restrict__ vT32, int H, int M, int nkv,
+                           uint8_t* __restrict__ kt, uint8_t* __restrict__ vt) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;    // one 16-byte chunk of K and of V^T per thread
+  const long long per_head = (long long)nkv * 128 * 8;
+  if (t >= per_head * H) return;
+  const int h = (int)(t / per_head); long long rem = t % per_head;
+  {  // K: row = token, chunk over d
+    const int tok = (int)(rem / 8), c16 = (int)(rem % 8);
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = tok < M ? k32[((size_t)h * M + tok) * 64 + c16 * 8 + i] : 0.f;
+    uint8_t* tile = kt + ((size_t)h * nkv + tok / 128) * TILE_BYTES;
+    store_t16_chunk(tile, tok % 128, c16, v);
+  }
+  {  // V^T: row = d, chunk over 8 tokens
+    const int d = (int)(rem % 64); const int tc8 = (int)(rem / 64);          // token chunk index over all padded tokens
+    const int tok0 = tc8 * 8, j = tok0 / 128, kbk = (tok0 % 128) / 64, c16 = (tok0 % 64) / 8;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = (tok0 + i) < M ? vT32[((size_t)h * 64 + d) * M + tok0 + i] : 0.f;
+    uint8_t* tile = vt + ((size_t)h * nkv + j) * TILE_BYTES + kbk * (TILE_BYTES / 2);
+    store_t16_chunk(tile, d, c16, v);
+  }
+}
+
+template <int EPI>
+int launch_gemm(hy3d_ctx* ctx, const GemmTC& g) {
+  HY3D_CUDA(ctx, cudaFuncSetAttribute(k_gemm_tc<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+  int tiles = g.Mb * g.Nb;
+  int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
+  k_gemm_tc<EPI><<<grid, GEMM_THREADS, GEMM_SMEM, ctx->stream>>>(g);
+  HY3D_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+int hy3d_tc_prepare_weights(hy3d_ctx* ctx) {
+  DecoderWeights& w = ctx->w;
+  if (w.D != 64 || w.W % 256 || (w.W * w.R) % 256) {
+    // the tcgen05 path is specialised to head_dim 64 and widths that tile by 256; other shapes can
+    // only run in HY3D_PRECISION_FP32_SIMT
+    w.t_qp = nullptr;
+    return 0;
+  }
+  const size_t W = w.W, R = w.R;
+  const size_t n_qp = W * 192, n_cq = W * W, n_cp = W * W, n_fc = R * W * W, n_mp = R * W * W;
+  HY3D_CUDA(ctx, w.tc.reserve((n_qp + n_cq + n_cp + n_fc + n_mp) * 2));
+  __half* base = w.tc.as<__half>();
+  __half* p_qp = base; __half* p_cq = p_qp + n_qp; __half* p_cp = p_cq + n_cq; __half* p_fc = p_cp + n_cp; __half* p_mp = p_fc + n_fc;
+  auto build = [&](const float* src, int N, int K, int ldw, int mode, __half* dst) -> int {
+    long long total = (long long)N * (K / 8);
+    k_build_b16<<<(unsigned)ceil_div64(total, 256), 256, 0, ctx->stream>>>(src, N, K, ldw, mode, w.E, reinterpret_cast<uint8_t*>(dst));
+    HY3D_LAUNCH_CHECK(ctx);
+    return 0;
+  };
+  if (int rc = build(w.qp_w, (int)W, 192, w.E, 1, p_qp)) return rc;
+  if (int rc = build(w.cq_w, (int)W, (int)W, (int)W, 0, p_cq)) return rc;
+  if (int rc = build(w.cproj_w, (int)W, (int)W, (int)W, 0, p_cp)) return rc;
+  if (int rc = build(w.fc_w, (int)(R * W), (int)W, (int)W, 0, p_fc)) return rc;
+  if (int rc = build(w.mp_w, (int)W, (int)(R * W), (int)(R * W), 0, p_mp)) return rc;
+  w.t_qp = p_qp; w.t_cq = p_cq; w.t_cproj = p_cp; w.t_fc = p_fc; w.t_mp = p_mp;
+  return 0;
+}
+
+int hy3d_tc_prepare_kv(hy3d_ctx* ctx) {
+  DecoderWeights& w = ctx->w;
+  if (!w.t_qp) return 0;
+  KVState& kv = ctx->kv;
+  const int nkv = kv.Mpad / 128;
+  size_t bytes = (size_t)w.H * nkv * TILE_BYTES;
+  HY3D_CUDA(ctx, kv.ktile.reserve(bytes));
+  HY3D_CUDA(ctx, kv.vtile.reserve(bytes));
+  long long total = (long long)w.H * nkv * 128 * 8;
+  k_build_kv<<<(unsigned)ceil_div64(total, 256), 256, 0, ctx->stream>>>(kv.k32.as<float>(), kv.v32.as<float>(), w.H, kv.M, nkv,
+                                                                        kv.ktile.as<uint8_t>(), kv.vtile.as<uint8_t>());
+  HY3D_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+int hy3d_decode_tc(hy3d_ctx* ctx, const QuerySource& src_in, long long n, float* d_out, int out_mode) {
+  DecoderWeights& w = ctx->w;
+  if (!w.t_qp)
+    return hy3d_fail(ctx, HY3D_ERR_UNSUPPORTED, "tcgen05 path needs head_dim 64 and widths that are multiples of 256");
+  const int W = w.W, H = w.H, R = w.R;
+  const long long CH = 131072;                                 // points per chunk (1024 tiles)
+  const long long chmax = n < CH ? (n + 127) / 128 * 128 : CH;
+  HY3D_CUDA(ctx, ctx->ws[2].reserve((size_t)chmax * W * 4));          // R32 residual stream
+  HY3D_CUDA(ctx, ctx->ws[3].reserve((size_t)chmax * W * 2));          // T16 a (embed / ln / attn out)
+  HY3D_CUDA(ctx, ctx->ws[4].reserve((size_t)chmax * W * 2));          // T16 q
+  HY3D_CUDA(ctx, ctx->ws[5].reserve((size_t)chmax * W * R * 2));      // T16 h
+  float* x = ctx->ws[2].as<float>();
+  uint8_t* ta = ctx->ws[3].as<uint8_t>();
+  uint8_t* tq = ctx->ws[4].as<uint8_t>();
+  uint8_t* th = ctx->ws[5].as<uint8_t>();
+  HY3D_CUDA(ctx, cudaFuncSetAttribute(k_attn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
+  const float pi_mul = w.include_pi ? 3.14159265358979323846f : 1.f;
+  for (long long p0 = 0; p0 < n; p0 += CH) {
+    const long long P = (n - p0 < CH) ? (n - p0) : CH;
+    const int Pb = (int)((P + 127) / 128);
+    QuerySource src = src_in;
+    if (src.mode == 0) src.xyz += 3 * p0;
+    else if (src.mode == 1) src.first += p0;
+    else src.index += p0;
+    k_embed_tc<<<Pb, 128, 0, ctx->stream>>>(src, P, w.F, pi_mul, ta);
+    HY3D_LAUNCH_CHECK(ctx);
+    GemmTC g{};
+    g.Mb = Pb;
+    // x0 = query_proj(e)
+    g.A = ta; g.B = reinterpret_cast<const uint8_t*>(w.t_qp); g.KB = 3; g.N = W; g.Nb = W / BN; g.bias = w.qp_b; g.Rout = x;
+    if (int rc = launch_gemm<EPI_X0>(ctx, g)) return rc;
+    const long long Pp = (long long)Pb * 128;
+    if (int rc = hy3d_debug_keep(ctx, 0, x, (size_t)Pp * W * 4, 1, Pp, W)) return rc;
+    k_ln_tc<<<Pb, 128, 0, ctx->stream>>>(x, W, w.ln1_w, w.ln1_b, 1e-6f, ta);
+    HY3D_LAUNCH_CHECK(ctx);
+    if (int rc = hy3d_debug_keep(ctx, 1, ta, (size_t)Pp * W * 2, 2, Pp, W)) return rc;
+    // q = q_norm(c_q(ln_1 x0)) * scale * log2e
+    g = GemmTC{}; g.Mb = Pb;
+    g.A = ta; g.B = reinterpret_cast<const uint8_t*>(w.t_cq); g.KB = W / 64; g.N = W; g.Nb = W / BN; g.bias = w.cq_b; g.Tout = tq;
+    g.qn_w = w.qn_w; g.qn_b = w.qn_b; g.qk_norm = w.qk_norm ? 1 : 0; g.qscale = rsqrtf((float)w.D) * LOG2E;
+    if (int rc = launch_gemm<EPI_Q>(ctx, g)) return rc;
+    if (int rc = hy3d_debug_keep(ctx, 2, tq, (size_t)Pp * W * 2, 2, Pp, W)) return rc;
+    {
+      AttnTC a{};
+      a.Q = tq; a.K = ctx->kv.ktile.as<uint8_t>(); a.V = ctx->kv.vtile.as<uint8_t>(); a.O = ta;
+      a.Pb = Pb; a.H = H; a.nkv = ctx->kv.Mpad / 128; a.ntok = ctx->kv.M;
+      int items = Pb * (H / 2);
+      int grid = items < ctx->num_sms ? items : ctx->num_sms;
+      k_attn_tc<<<grid, ATT_THREADS, ATT_SMEM, ctx->stream>>>(a);
+      HY3D_LAUNCH_CHECK(ctx);
+    }
+    if (int rc = hy3d_debug_keep(ctx, 3, ta, (size_t)Pp * W * 2, 2, Pp, W)) return rc;
+    // x1 = x0 + c_proj(attn)
+    g = GemmTC{}; g.Mb = Pb;
+    g.A = ta; g.B = reinterpret_cast<const uint8_t*>(w.t_cproj); g.KB = W / 64; g.N = W; g.Nb = W / BN; g.bias = w.cproj_b; g.Rin = x; g.Rout = x;
+    if (int rc = launch_gemm<EPI_RES>(ctx, g)) return rc;
+    if (int rc = hy3d_debug_keep(ctx, 4, x, (size_t)Pp * W * 4, 1, Pp, W)) return rc;
+    k_ln_tc<<<Pb, 128, 0, ctx->stream>>>(x, W, w.ln3_w, w.ln3_b, 1e-6f, ta);
+    HY3D_LAUNCH_CHECK(ctx);
+    if (int rc = hy3d_debug_keep(ctx, 5, ta, (size_t)Pp * W * 2, 2, Pp, W)) return rc;
+    // h = gelu(c_fc(ln_3 x1))
+    g = GemmTC{}; g.Mb = Pb;
+    g.A = ta; g.B = reinterpret_cast<const uint8_t*>(w.t_fc); g.KB = W / 64; g.N = W * R; g.Nb = W * R / BN; g.bias = w.fc_b; g.Tout = th;
+    if (int rc = launch_gemm<EPI_GELU>(ctx, g)) return rc;
+    if (int rc = hy3d_debug_keep(ctx, 6, th, (size_t)Pp * W * R * 2, 2, Pp, W * R)) return rc;
+    // x2 = x1 + c_proj(h)
+    g = GemmTC{}; g.Mb = Pb;
+    g.A = th; g.B = reinterpret_cast<const uint8_t*>(w.t_mp); g.KB = W * R / 64; g.N = W; g.Nb = W / BN; g.bias = w.mp_b; g.Rin = x; g.Rout = x;
+    if (int rc = launch_gemm<EPI_RES>(ctx, g)) return rc;
+    if (int rc = hy3d_debug_keep(ctx, 7, x, (size_t)Pp * W * 4, 1, Pp, W)) return rc;
+    float* outp = d_out + (out_mode == 0 ? p0 : 0);
+    k_head_tc<<<Pb, 128, 0, ctx->stream>>>(x, W, w.ln_post ? w.lnp_w : nullptr, w.lnp_b, w.out_w, w.out_b, src, P, outp, out_mode);
+    HY3D_LAUNCH_CHECK(ctx);
+  }
+  return 0;
+}
+
+extern "C" int hy3d_debug_watchdog(hy3d_ctx* ctx, int32_t h_out[8]) {
+  if (!ctx || !h_out) return HY3D_ERR_ARG;
+  HY3D_CUDA(ctx, cudaSetDevice(ctx->device));
+  HY3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  HY3D_CUDA(ctx, cudaMemcpyFromSymbol(h_out, hy3d_wd, sizeof(int) * 8));
+  int zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  HY3D_CUDA(ctx, cudaMemcpyToSymbol(hy3d_wd, zero, sizeof(zero)));
+  return HY3D_OK;
+}

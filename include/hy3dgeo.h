@@ -1,0 +1,146 @@
+/* hy3dgeo.h — C-ABI of libhy3dgeo.so: B200-native (sm_100a) geometry decoding for
+ * Hunyuan3D-2 (latents -> occupancy grid -> mesh).
+ *
+ * The reference has no FFI for this path: it is Python calling torch and skimage.
+ * Each entry point below names the reference Python interface it replaces
+ * (paths relative to /root/reference/hy3dgen/shapegen/models/autoencoders/).
+ * The host-side mirror of those interfaces (same class names, kwargs and error
+ * behaviour) lives in hunyuan3d-2_b200/{volume_decoders,surface_extractors}.py
+ * and binds this header through ctypes.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every `const float* d_*` / `float* d_*` is a
+ *     DEVICE pointer on the context's device, `h_*` is a HOST pointer;
+ *   - all work is enqueued on the context's stream (hy3d_set_stream); the only
+ *     host synchronisations are the explicit size read-backs documented below;
+ *   - return value 0 = success, negative = error (hy3d_last_error gives text);
+ *     nothing throws across the ABI;
+ *   - a context is NOT thread-safe: one context per (host thread, device);
+ *   - there is no CPU fallback anywhere behind this ABI.
+ */
+#ifndef HY3DGEO_H
+#define HY3DGEO_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HY3D_OK 0
+#define HY3D_ERR_CUDA (-1)
+#define HY3D_ERR_ARG (-2)
+#define HY3D_ERR_STATE (-3)
+#define HY3D_ERR_UNSUPPORTED (-4)
+
+typedef struct hy3d_ctx hy3d_ctx;
+
+/* Arithmetic of the decoder's dense contractions. */
+#define HY3D_PRECISION_FP32_SIMT 0 /* fp32 CUDA-core kernels: exact-order reference on the device      */
+#define HY3D_PRECISION_FP16_TC 1   /* fp16 operands, fp32 accumulate on tcgen05/TMEM (the product path) */
+
+/* Weights of CrossAttentionDecoder (attention_blocks.py:435-476), fp32 DEVICE pointers in
+ * PyTorch nn.Linear layout [out_features, in_features] row-major, names as in its
+ * state_dict.  Optional tensors are NULL when absent. */
+typedef struct hy3d_decoder_desc {
+  int32_t width;        /* decoder width Wd = query_proj.weight.shape[0]                   */
+  int32_t heads;        /* cross_attn_decoder.attn.heads                                  */
+  int32_t mlp_ratio;    /* c_fc.weight.shape[0] / Wd                                      */
+  int32_t latent_width; /* width of the incoming latents (= Wd * downsample_ratio)        */
+  int32_t num_freqs;    /* FourierEmbedder.num_freqs (attention_blocks.py:72-98)          */
+  int32_t include_pi;   /* frequencies *= pi                                              */
+  int32_t ln_post;      /* enable_ln_post (attention_blocks.py:471-473)                   */
+  int32_t qk_norm;      /* q_norm / k_norm present (attention_blocks.py:197-198)          */
+  const float* query_proj_w;   const float* query_proj_b;     /* [Wd, 3*(2F+1)], [Wd]    */
+  const float* latents_proj_w; const float* latents_proj_b;   /* [Wd, latent_width] / NULL */
+  const float* ln1_w; const float* ln1_b;                     /* [Wd]                     */
+  const float* ln2_w; const float* ln2_b;                     /* [Wd]                     */
+  const float* ln3_w; const float* ln3_b;                     /* [Wd]                     */
+  const float* c_q_w;    const float* c_q_b;                  /* [Wd, Wd], bias or NULL   */
+  const float* c_kv_w;   const float* c_kv_b;                 /* [2Wd, Wd], bias or NULL  */
+  const float* c_proj_w; const float* c_proj_b;               /* [Wd, Wd], [Wd]           */
+  const float* q_norm_w; const float* q_norm_b;               /* [Wd/heads] or NULL       */
+  const float* k_norm_w; const float* k_norm_b;               /* [Wd/heads] or NULL       */
+  const float* c_fc_w;     const float* c_fc_b;               /* [r*Wd, Wd], [r*Wd]       */
+  const float* mlp_proj_w; const float* mlp_proj_b;           /* [Wd, r*Wd], [Wd]         */
+  const float* ln_post_w;  const float* ln_post_b;            /* [Wd] or NULL             */
+  const float* out_w;      const float* out_b;                /* [1, Wd], [1]             */
+} hy3d_decoder_desc;
+
+/* ---- context -------------------------------------------------------------------------- */
+int hy3d_create(int device, void* cuda_stream, hy3d_ctx** out);
+void hy3d_destroy(hy3d_ctx* ctx);
+int hy3d_set_stream(hy3d_ctx* ctx, void* cuda_stream);
+const char* hy3d_last_error(const hy3d_ctx* ctx);
+/* HY3D_PRECISION_*; default HY3D_PRECISION_FP16_TC. */
+int hy3d_set_precision(hy3d_ctx* ctx, int precision);
+/* Count of kernels this library has launched on ctx since creation (bench `gpu_launches`). */
+int64_t hy3d_launch_count(const hy3d_ctx* ctx);
+
+/* ---- decoder: replaces CrossAttentionDecoder.forward (attention_blocks.py:483-493) ---- */
+/* Copies / re-lays-out the weights into the context (fp16 UMMA tiles + fp32 originals). */
+int hy3d_set_decoder_weights(hy3d_ctx* ctx, const hy3d_decoder_desc* desc);
+/* Per-latent work hoisted out of the query loop: [latents_proj] -> ln_2 -> c_kv -> k_norm
+ * (attention_blocks.py:487-488, 296, 257, 205-211).  d_latents: fp32 [M, latent_width]. */
+int hy3d_prepare_kv(hy3d_ctx* ctx, const float* d_latents, int32_t M);
+/* logits for explicit points.  d_xyz: fp32 [n,3]; d_out: fp32 [n]. */
+int hy3d_decode_points(hy3d_ctx* ctx, const float* d_xyz, int64_t n, float* d_out);
+/* Dense grid, replaces VanillaVolumeDecoder.__call__'s loop (volume_decoders.py:162-180) for
+ * the flat index range [first, first+count) of an [n0,n1,n2] grid (index (i*n1+j)*n2+k).
+ * h_axis{0,1,2}: HOST per-axis coordinate tables (np.linspace, volume_decoders.py:131-133).
+ * d_out receives `count` logits (d_out[0] is flat index `first`). */
+int hy3d_decode_dense(hy3d_ctx* ctx, const float* h_axis0, const float* h_axis1, const float* h_axis2,
+                      int32_t n0, int32_t n1, int32_t n2, int64_t first, int64_t count, float* d_out);
+/* Sparse list, replaces the refined-level loops (volume_decoders.py:262-274, 394-431):
+ * point p = float32(ijk) * cell + bmin (fp32 mul then add), ijk from the flat index
+ * d_index[q] of an [n0,n1,n2] grid; result scattered to d_grid[d_index[q]].
+ * Entries with d_index[q] < 0 are padding and are skipped. */
+int hy3d_decode_list(hy3d_ctx* ctx, const int32_t* d_index, int64_t n, int32_t n0, int32_t n1, int32_t n2,
+                     const float h_cell[3], const float h_bmin[3], float* d_grid);
+
+/* ---- octree refinement: replaces volume_decoders.py:29-119 and :245-260 / :376-391 ----- */
+/* Active fine voxels of one coarse->fine step: near-surface | band mask,
+ * dilation, x2 up-sampling, dilation, ordered compaction.  d_coarse: fp32 [n,n,n] (sentinel
+ * -10000 = unvisited).  Writes the lexicographically ordered flat fine indices (grid
+ * [2n-1]^3) to d_index (capacity `cap`), returns their number in *h_count (HOST; this
+ * call synchronises the stream once).  If the count exceeds cap nothing is written
+ * past cap and *h_count still holds the true count. */
+int hy3d_refine_level(hy3d_ctx* ctx, const float* d_coarse, int32_t n, float mc_level, int32_t last_level,
+                      int32_t* d_index, int64_t cap, int64_t* h_count);
+int hy3d_fill(hy3d_ctx* ctx, float* d_grid, int64_t n, float value);
+/* grid[grid == sentinel] = NaN (volume_decoders.py:275, :433). */
+int hy3d_sentinel_to_nan(hy3d_ctx* ctx, float* d_grid, int64_t n, float sentinel);
+
+/* ---- marching cubes: replaces MCSurfaceExtractor.run (surface_extractors.py:68-76) ------ */
+/* Phase 1: classify + count.  d_grid: fp32 [n0,n1,n2]; inside test `v - level > 0`, NaN =>
+ * outside.  Returns vertex/face counts and the finite min/max of the field in HOST
+ * variables (synchronises the stream once).  h_minmax[2] = 1 if the grid holds NaN. */
+int hy3d_mc_count(hy3d_ctx* ctx, const float* d_grid, int32_t n0, int32_t n1, int32_t n2, float level,
+                  int64_t* h_num_verts, int64_t* h_num_faces, float h_minmax[3]);
+/* Phase 2: emit the welded, indexed mesh of the grid given to the last hy3d_mc_count.
+ * Vertex v (index units, array-axis order) is written as
+ *   float32( double(v) / h_div[a] * h_mul[a] + h_add[a] )   per axis a
+ * which is the reference's `vertices / grid_size * bbox_size + bbox_min` (float64, :75).
+ * d_verts: fp32 [V,3]; d_faces: int32 [F,3]. */
+int hy3d_mc_emit(hy3d_ctx* ctx, const double h_div[3], const double h_mul[3], const double h_add[3],
+                 float* d_verts, int32_t* d_faces);
+/* Table-independent classification for parity tests: 8-bit case per cube, [n0-1,n1-1,n2-1]. */
+int hy3d_mc_cases(hy3d_ctx* ctx, const float* d_grid, int32_t n0, int32_t n1, int32_t n2, float level,
+                  uint8_t* d_cases);
+
+/* ---- diagnostics ---------------------------------------------------------------------- */
+/* Synchronises the stream and returns + clears the tensor-path watchdog record:
+ * h_out[0] != 0 means an mbarrier wait timed out inside a tcgen05 kernel (results of that
+ * launch are invalid); h_out[1..4] = block, thread, barrier shared address, parity. */
+int hy3d_debug_watchdog(hy3d_ctx* ctx, int32_t h_out[8]);
+/* Keep (enable=1) the per-stage activations of the last decoded chunk for hy3d_debug_fetch.
+ * Stage ids: 0 x0, 1 ln_1(x0), 2 q after q_norm (the tcgen05 path stores q*scale*log2e),
+ * 3 attention output, 4 x1, 5 ln_3(x1), 6 MLP hidden, 7 x2.  Costs one device copy per stage. */
+int hy3d_debug_retain(hy3d_ctx* ctx, int enable);
+/* Row-major fp32 [rows, *h_width] copy of a retained stage, whatever its internal layout. */
+int hy3d_debug_fetch(hy3d_ctx* ctx, int stage, float* d_out, int64_t rows, int32_t* h_width);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HY3DGEO_H */
