@@ -1,0 +1,95 @@
+"""CPU: the C-ABI library loads and exports every symbol include/hy3dgeo.h declares (no compute
+without a GPU), and the host-side mirror keeps the reference's interface and error behaviour."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import hy3dgeo
+from hy3dgeo import _lib, weights as W
+from hy3dgeo.surface_extractors import (Latent2MeshOutput, MCSurfaceExtractor, SurfaceExtractor, SurfaceExtractors)
+from hy3dgeo.volume_decoders import (FlashVDMVolumeDecoding, HierarchicalVolumeDecoding, VanillaVolumeDecoder,
+                                     axis_tables, flash_levels, hierarchy_levels)
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "hy3dgeo.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(hy3d_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load_library()
+    names = header_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/hy3dgeo.h but not exported"
+    assert set(names) == set(_lib.SYMBOLS), "ctypes table and header disagree"
+
+
+def test_no_cpu_fallback_paths():
+    with pytest.raises(RuntimeError):
+        VanillaVolumeDecoder()(torch.zeros(1, 4, 8), hy3dgeo.GeoDecoder({}, W.MINI), octree_resolution=8)
+    with pytest.raises(RuntimeError):
+        _lib.get_context("cpu")
+    out = MCSurfaceExtractor()(torch.zeros(2, 5, 5, 5), mc_level=0.0, bounds=1.01, octree_resolution=4)
+    assert out == [None, None]                      # reference convention: exception -> None per item
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "hunyuan3d-2_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            text = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in re.sub(r'""".*?"""', "", text, flags=re.S), fn
+
+
+def test_level_lists_and_tables():
+    assert hierarchy_levels(384) == [96, 192, 384] and hierarchy_levels(32, 15) == [16, 32]
+    assert hierarchy_levels(40) == [40]
+    assert flash_levels(384) == [95, 190, 380] and flash_levels(512) == [63, 126, 252, 504]
+    ax = axis_tables(1.01, 128)
+    assert ax[0].dtype == np.float32 and len(ax[2]) == 129 and ax[1][0] == np.float32(-1.01) and ax[1][-1] == np.float32(1.01)
+    ax = axis_tables([-1, -2, -3, 1, 2, 3], 4)
+    assert np.allclose(ax[1], [-2, -1, 0, 1, 2])
+
+
+def test_interface_mirrors_reference():
+    assert set(SurfaceExtractors) == {"mc", "dmc"} and SurfaceExtractors["mc"] is MCSurfaceExtractor
+    with pytest.raises(ValueError):
+        FlashVDMVolumeDecoding("median")
+    gs, bmin, bsize = SurfaceExtractor()._compute_box_stat(1.01, 384)
+    assert gs == [385, 385, 385] and np.allclose(bsize, 2.02) and np.allclose(bmin, -1.01)
+    o = Latent2MeshOutput(mesh_v=1, mesh_f=2)
+    assert (o.mesh_v, o.mesh_f) == (1, 2)
+    import inspect
+    for cls, names in [(VanillaVolumeDecoder, ["latents", "geo_decoder", "bounds", "num_chunks", "octree_resolution", "enable_pbar"]),
+                       (HierarchicalVolumeDecoding, ["latents", "geo_decoder", "bounds", "num_chunks", "mc_level",
+                                                     "octree_resolution", "min_resolution", "enable_pbar"]),
+                       (FlashVDMVolumeDecoding, ["latents", "geo_decoder", "bounds", "num_chunks", "mc_level",
+                                                 "octree_resolution", "min_resolution", "mini_grid_num", "enable_pbar"])]:
+        sig = inspect.signature(cls.__call__)
+        assert list(sig.parameters)[1:1 + len(names)] == names
+        assert sig.parameters["bounds"].default == 1.01 and sig.parameters["num_chunks"].default == 10000
+
+
+def test_type_error_for_arbitrary_callable():
+    from hy3dgeo.volume_decoders import _decoder_identity
+    with pytest.raises(TypeError):
+        _decoder_identity(lambda queries, latents: None)
+
+
+def test_synthetic_state_dict_keys_and_config_roundtrip():
+    for cfg in (W.MINI, W.MINI_TURBO):
+        sd = W.synthetic_state_dict(cfg, with_transformer=False)
+        gd = hy3dgeo.GeoDecoder(W.geo_decoder_state(sd), cfg)
+        back = W.config_from_geo_decoder(gd)
+        assert (back.dec_width, back.dec_heads, back.geo_decoder_mlp_expand_ratio) == \
+               (cfg.dec_width, cfg.dec_heads, cfg.geo_decoder_mlp_expand_ratio)
+        assert back.geo_decoder_ln_post == cfg.geo_decoder_ln_post and back.dec_qk_norm == cfg.dec_qk_norm
+        assert back.width == cfg.width and back.num_freqs == 8 and back.include_pi is False
+    assert sum(v.numel() for v in W.synthetic_state_dict(W.MINI).values()) == 214212865
