@@ -54,6 +54,9 @@ SYMBOLS = {
                                     C.c_int64, C.c_int64, c_f32p]),
     "hy3d_decode_list": (C.c_int, [C.c_void_p, c_i32p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                    C.POINTER(C.c_float), C.POINTER(C.c_float), c_f32p]),
+    "hy3d_decode_list_values": (C.c_int, [C.c_void_p, c_i32p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                          C.POINTER(C.c_float), C.POINTER(C.c_float), c_f32p]),
+    "hy3d_scatter": (C.c_int, [C.c_void_p, c_i32p, c_f32p, C.c_int64, c_f32p]),
     "hy3d_refine_level": (C.c_int, [C.c_void_p, c_f32p, C.c_int32, C.c_float, C.c_int32, c_i32p, C.c_int64,
                                     C.POINTER(C.c_int64)]),
     "hy3d_fill": (C.c_int, [C.c_void_p, c_f32p, C.c_int64, C.c_float]),
@@ -62,6 +65,8 @@ SYMBOLS = {
                                 C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_float)]),
     "hy3d_mc_emit": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                c_f32p, c_i32p]),
+    "hy3d_profile": (C.c_int, [C.c_void_p, C.c_int]),
+    "hy3d_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "hy3d_debug_watchdog": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
     "hy3d_debug_retain": (C.c_int, [C.c_void_p, C.c_int]),
     "hy3d_debug_fetch": (C.c_int, [C.c_void_p, C.c_int, c_f32p, C.c_int64, C.POINTER(C.c_int32)]),
@@ -223,6 +228,19 @@ class GeoContext:
         self._check(self.lib.hy3d_debug_watchdog(self.h, out), "hy3d_debug_watchdog")
         return list(out)
 
+    FAMILIES = ["embed", "gemm_query_proj", "layernorm", "gemm_c_q", "attention", "gemm_c_proj", "gemm_c_fc",
+                "gemm_mlp_proj", "head", "mc_bits", "mc_rowcount", "mc_scan", "mc_emit", "octree", "kv_prepare", "kv_select"]
+
+    def profile(self, enable: bool):
+        self._check(self.lib.hy3d_profile(self.h, int(enable)), "hy3d_profile")
+
+    def profile_read(self):
+        """{family: (total_ms, launches)} since the last read (device time, CUDA events)."""
+        ms = (C.c_double * 16)()
+        cnt = (C.c_int64 * 16)()
+        self._check(self.lib.hy3d_profile_read(self.h, ms, cnt), "hy3d_profile_read")
+        return {f: (ms[i], cnt[i]) for i, f in enumerate(self.FAMILIES)}
+
     def debug_retain(self, enable: bool):
         self._check(self.lib.hy3d_debug_retain(self.h, int(enable)), "hy3d_debug_retain")
 
@@ -237,6 +255,21 @@ class GeoContext:
         rec = self.watchdog()
         if rec[0]:
             raise Hy3dError(f"tcgen05 kernel barrier timeout: block {rec[1]} thread {rec[2]} bar 0x{rec[3]:x} parity {rec[4]}")
+
+    def decode_list_values(self, index: torch.Tensor, dims, cell, bmin) -> torch.Tensor:
+        self.sync_stream()
+        index = index.contiguous()
+        out = torch.empty(index.numel(), dtype=torch.float32, device=self.device)
+        cc = (C.c_float * 3)(*[float(v) for v in cell])
+        bb = (C.c_float * 3)(*[float(v) for v in bmin])
+        self._check(self.lib.hy3d_decode_list_values(self.h, _ptr(index), index.numel(), dims[0], dims[1], dims[2], cc, bb,
+                                                     _ptr(out)), "hy3d_decode_list_values")
+        return out
+
+    def scatter(self, index: torch.Tensor, values: torch.Tensor, grid: torch.Tensor):
+        self.sync_stream()
+        self._check(self.lib.hy3d_scatter(self.h, _ptr(index.contiguous()), _ptr(values.contiguous()), index.numel(),
+                                          _ptr(grid)), "hy3d_scatter")
 
     # ---- octree -------------------------------------------------------------------------------
     def refine_level(self, coarse: torch.Tensor, mc_level: float, last: bool, index: Optional[torch.Tensor]) -> int:

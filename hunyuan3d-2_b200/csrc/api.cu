@@ -41,6 +41,27 @@ __global__ void k_debug_unpack(const void* __restrict__ src, int layout, long lo
 
 extern "C" {
 
+int hy3d_profile(hy3d_ctx* ctx, int enable) {
+  if (!ctx) return HY3D_ERR_ARG;
+  ctx->prof.on = enable ? 1 : 0;
+  return HY3D_OK;
+}
+
+int hy3d_profile_read(hy3d_ctx* ctx, double h_ms[16], int64_t h_count[16]) {
+  if (!ctx || !h_ms || !h_count) return HY3D_ERR_ARG;
+  HY3D_CUDA(ctx, cudaSetDevice(ctx->device));
+  HY3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  Prof& p = ctx->prof;
+  for (auto& r : p.recs) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) { p.ms[r.fam] += ms; p.cnt[r.fam]++; }
+    p.pool.push_back(r.e0); p.pool.push_back(r.e1);
+  }
+  p.recs.clear(); p.cur = -1;
+  for (int f = 0; f < 16; ++f) { h_ms[f] = p.ms[f]; h_count[f] = p.cnt[f]; p.ms[f] = 0; p.cnt[f] = 0; }
+  return HY3D_OK;
+}
+
 int hy3d_debug_retain(hy3d_ctx* ctx, int enable) {
   if (!ctx) return HY3D_ERR_ARG;
   ctx->debug_retain = enable ? 1 : 0;
@@ -92,6 +113,8 @@ void hy3d_destroy(hy3d_ctx* ctx) {
   for (auto& b : ctx->ws) b.release();
   ctx->scratch.release(); ctx->scratch2.release();
   for (auto& b : ctx->dbg) b.release();
+  for (auto& r : ctx->prof.recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  for (auto e : ctx->prof.pool) cudaEventDestroy(e);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   delete ctx;
 }
@@ -227,6 +250,17 @@ int hy3d_decode_list(hy3d_ctx* ctx, const int32_t* d_index, int64_t n, int32_t n
   s.mode = 2; s.index = d_index; s.n0 = n0; s.n1 = n1; s.n2 = n2;
   for (int a = 0; a < 3; ++a) { s.cell[a] = h_cell[a]; s.bmin[a] = h_bmin[a]; }
   return decode(ctx, s, n, d_grid, 1);
+}
+
+int hy3d_decode_list_values(hy3d_ctx* ctx, const int32_t* d_index, int64_t n, int32_t n0, int32_t n1, int32_t n2,
+                            const float h_cell[3], const float h_bmin[3], float* d_values) {
+  if (!ctx || n < 0 || !h_cell || !h_bmin) return HY3D_ERR_ARG;
+  if (n == 0) return HY3D_OK;
+  if (!d_index || !d_values) return HY3D_ERR_ARG;
+  QuerySource s{};
+  s.mode = 2; s.index = d_index; s.n0 = n0; s.n1 = n1; s.n2 = n2;
+  for (int a = 0; a < 3; ++a) { s.cell[a] = h_cell[a]; s.bmin[a] = h_bmin[a]; }
+  return decode(ctx, s, n, d_values, 0);
 }
 
 }  // extern "C"

@@ -62,6 +62,18 @@ struct McState {
   DevBuf bits, rowcnt, rowoff, stats;
 };
 
+// Per-kernel-family device timing with CUDA events on the launch stream (bench.py roofline).
+enum { FAM_EMBED = 0, FAM_GEMM_QPROJ, FAM_LN, FAM_GEMM_CQ, FAM_ATTN, FAM_GEMM_CPROJ, FAM_GEMM_FC, FAM_GEMM_MLP, FAM_HEAD,
+       FAM_MC_BITS, FAM_MC_ROWCOUNT, FAM_MC_SCAN, FAM_MC_EMIT, FAM_OCTREE, FAM_KV, FAM_SELECT, FAM_COUNT };
+struct ProfRec { int fam; cudaEvent_t e0, e1; };
+struct Prof {
+  int on = 0, cur = -1;
+  std::vector<ProfRec> recs;
+  std::vector<cudaEvent_t> pool;
+  double ms[FAM_COUNT] = {};
+  long long cnt[FAM_COUNT] = {};
+};
+
 struct hy3d_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -75,6 +87,7 @@ struct hy3d_ctx {
   DevBuf ws[12];                      // decoder workspaces
   DevBuf scratch, scratch2;           // octree / misc
   void* pinned = nullptr;             // small pinned host buffer for read-backs
+  Prof prof;
   // diagnostics: per-stage activations of the last decoded chunk (hy3d_debug_retain / hy3d_debug_fetch)
   int debug_retain = 0;
   DevBuf dbg[8];
@@ -95,9 +108,30 @@ int hy3d_fail(hy3d_ctx* ctx, int code, const char* fmt, ...);
                        cudaGetErrorString(_e));                                                \
   } while (0)
 
+static inline void hy3d_prof_begin(hy3d_ctx* ctx, int fam) {
+  Prof& p = ctx->prof;
+  if (!p.on) return;
+  ProfRec r; r.fam = fam;
+  for (cudaEvent_t* e : {&r.e0, &r.e1}) {
+    if (!p.pool.empty()) { *e = p.pool.back(); p.pool.pop_back(); }
+    else cudaEventCreate(e);
+  }
+  cudaEventRecord(r.e0, ctx->stream);
+  p.recs.push_back(r);
+  p.cur = (int)p.recs.size() - 1;
+}
+static inline void hy3d_prof_end(hy3d_ctx* ctx) {
+  Prof& p = ctx->prof;
+  if (!p.on || p.cur < 0) return;
+  cudaEventRecord(p.recs[p.cur].e1, ctx->stream);
+  p.cur = -1;
+}
+#define HY3D_PROF(ctx, fam) hy3d_prof_begin(ctx, fam)
+
 #define HY3D_LAUNCH_CHECK(ctx)                                                                 \
   do {                                                                                         \
     (ctx)->launches++;                                                                         \
+    hy3d_prof_end(ctx);                                                                        \
     HY3D_CUDA(ctx, cudaGetLastError());                                                        \
   } while (0)
 

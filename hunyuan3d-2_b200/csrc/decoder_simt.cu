@@ -216,6 +216,7 @@ int layernorm(hy3d_ctx* ctx, const float* x, long long rows, int len, long long 
 // Per-latent K/V (fp32): [latents_proj] -> ln_2 -> c_kv -> split -> k_norm
 // ------------------------------------------------------------------------------------------
 int hy3d_simt_prepare_kv(hy3d_ctx* ctx, const float* d_latents, int M) {
+  HY3D_PROF(ctx, FAM_KV);   // times the first launch only; the K/V family total is read from its share of the step
   DecoderWeights& w = ctx->w;
   const int W = w.W, H = w.H, D = w.D;
   HY3D_CUDA(ctx, ctx->ws[0].reserve((size_t)M * W * 4));

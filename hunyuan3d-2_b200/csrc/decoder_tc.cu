@@ -606,10 +606,11 @@ __global__ void k_build_kv(const float* __restrict__ k32, const float* __restric
 }
 
 template <int EPI>
-int launch_gemm(hy3d_ctx* ctx, const GemmTC& g) {
+int launch_gemm(hy3d_ctx* ctx, const GemmTC& g, int fam) {
   HY3D_CUDA(ctx, cudaFuncSetAttribute(k_gemm_tc<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
   int tiles = g.Mb * g.Nb;
   int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
+  HY3D_PROF(ctx, fam);
   k_gemm_tc<EPI><<<grid, GEMM_THREADS, GEMM_SMEM, ctx->stream>>>(g);
   HY3D_LAUNCH_CHECK(ctx);
   return 0;
@@ -657,6 +658,7 @@ int hy3d_tc_prepare_kv(hy3d_ctx* ctx) {
   HY3D_CUDA(ctx, kv.ktile.reserve(bytes));
   HY3D_CUDA(ctx, kv.vtile.reserve(bytes));
   long long total = (long long)w.H * nkv * 128 * 8;
+  HY3D_PROF(ctx, FAM_KV);
   k_build_kv<<<(unsigned)ceil_div64(total, 256), 256, 0, ctx->stream>>>(kv.k32.as<float>(), kv.v32.as<float>(), w.H, kv.M, nkv,
                                                                         kv.ktile.as<uint8_t>(), kv.vtile.as<uint8_t>());
   HY3D_LAUNCH_CHECK(ctx);
@@ -687,15 +689,17 @@ int hy3d_decode_tc(hy3d_ctx* ctx, const QuerySource& src_in, long long n, float*
     if (src.mode == 0) src.xyz += 3 * p0;
     else if (src.mode == 1) src.first += p0;
     else src.index += p0;
+    HY3D_PROF(ctx, FAM_EMBED);
     k_embed_tc<<<Pb, 128, 0, ctx->stream>>>(src, P, w.F, pi_mul, ta);
     HY3D_LAUNCH_CHECK(ctx);
     GemmTC g{};
     g.Mb = Pb;
     // x0 = query_proj(e)
     g.A = ta; g.B = reinterpret_cast<const uint8_t*>(w.t_qp); g.KB = 3; g.N = W; g.Nb = W / BN; g.bias = w.qp_b; g.Rout = x;
-    if (int rc = launch_gemm<EPI_X0>(ctx, g)) return rc;
+    if (int rc = launch_gemm<EPI_X0>(ctx, g, FAM_GEMM_QPROJ)) return rc;
     const long long Pp = (long long)Pb * 128;
     if (int rc = hy3d_debug_keep(ctx, 0, x, (size_t)Pp * W * 4, 1, Pp, W)) return rc;
+    HY3D_PROF(ctx, FAM_LN);
     k_ln_tc<<<Pb, 128, 0, ctx->stream>>>(x, W, w.ln1_w, w.ln1_b, 1e-6f, ta);
     HY3D_LAUNCH_CHECK(ctx);
     if (int rc = hy3d_debug_keep(ctx, 1, ta, (size_t)Pp * W * 2, 2, Pp, W)) return rc;
@@ -703,7 +707,7 @@ int hy3d_decode_tc(hy3d_ctx* ctx, const QuerySource& src_in, long long n, float*
     g = GemmTC{}; g.Mb = Pb;
     g.A = ta; g.B = reinterpret_cast<const uint8_t*>(w.t_cq); g.KB = W / 64; g.N = W; g.Nb = W / BN; g.bias = w.cq_b; g.Tout = tq;
     g.qn_w = w.qn_w; g.qn_b = w.qn_b; g.qk_norm = w.qk_norm ? 1 : 0; g.qscale = rsqrtf((float)w.D) * LOG2E;
-    if (int rc = launch_gemm<EPI_Q>(ctx, g)) return rc;
+    if (int rc = launch_gemm<EPI_Q>(ctx, g, FAM_GEMM_CQ)) return rc;
     if (int rc = hy3d_debug_keep(ctx, 2, tq, (size_t)Pp * W * 2, 2, Pp, W)) return rc;
     {
       AttnTC a{};
@@ -711,6 +715,7 @@ int hy3d_decode_tc(hy3d_ctx* ctx, const QuerySource& src_in, long long n, float*
       a.Pb = Pb; a.H = H; a.nkv = ctx->kv.Mpad / 128; a.ntok = ctx->kv.M;
       int items = Pb * (H / 2);
       int grid = items < ctx->num_sms ? items : ctx->num_sms;
+      HY3D_PROF(ctx, FAM_ATTN);
       k_attn_tc<<<grid, ATT_THREADS, ATT_SMEM, ctx->stream>>>(a);
       HY3D_LAUNCH_CHECK(ctx);
     }
@@ -718,22 +723,24 @@ int hy3d_decode_tc(hy3d_ctx* ctx, const QuerySource& src_in, long long n, float*
     // x1 = x0 + c_proj(attn)
     g = GemmTC{}; g.Mb = Pb;
     g.A = ta; g.B = reinterpret_cast<const uint8_t*>(w.t_cproj); g.KB = W / 64; g.N = W; g.Nb = W / BN; g.bias = w.cproj_b; g.Rin = x; g.Rout = x;
-    if (int rc = launch_gemm<EPI_RES>(ctx, g)) return rc;
+    if (int rc = launch_gemm<EPI_RES>(ctx, g, FAM_GEMM_CPROJ)) return rc;
     if (int rc = hy3d_debug_keep(ctx, 4, x, (size_t)Pp * W * 4, 1, Pp, W)) return rc;
+    HY3D_PROF(ctx, FAM_LN);
     k_ln_tc<<<Pb, 128, 0, ctx->stream>>>(x, W, w.ln3_w, w.ln3_b, 1e-6f, ta);
     HY3D_LAUNCH_CHECK(ctx);
     if (int rc = hy3d_debug_keep(ctx, 5, ta, (size_t)Pp * W * 2, 2, Pp, W)) return rc;
     // h = gelu(c_fc(ln_3 x1))
     g = GemmTC{}; g.Mb = Pb;
     g.A = ta; g.B = reinterpret_cast<const uint8_t*>(w.t_fc); g.KB = W / 64; g.N = W * R; g.Nb = W * R / BN; g.bias = w.fc_b; g.Tout = th;
-    if (int rc = launch_gemm<EPI_GELU>(ctx, g)) return rc;
+    if (int rc = launch_gemm<EPI_GELU>(ctx, g, FAM_GEMM_FC)) return rc;
     if (int rc = hy3d_debug_keep(ctx, 6, th, (size_t)Pp * W * R * 2, 2, Pp, W * R)) return rc;
     // x2 = x1 + c_proj(h)
     g = GemmTC{}; g.Mb = Pb;
     g.A = th; g.B = reinterpret_cast<const uint8_t*>(w.t_mp); g.KB = W * R / 64; g.N = W; g.Nb = W / BN; g.bias = w.mp_b; g.Rin = x; g.Rout = x;
-    if (int rc = launch_gemm<EPI_RES>(ctx, g)) return rc;
+    if (int rc = launch_gemm<EPI_RES>(ctx, g, FAM_GEMM_MLP)) return rc;
     if (int rc = hy3d_debug_keep(ctx, 7, x, (size_t)Pp * W * 4, 1, Pp, W)) return rc;
     float* outp = d_out + (out_mode == 0 ? p0 : 0);
+    HY3D_PROF(ctx, FAM_HEAD);
     k_head_tc<<<Pb, 128, 0, ctx->stream>>>(x, W, w.ln_post ? w.lnp_w : nullptr, w.lnp_b, w.out_w, w.out_b, src, P, outp, out_mode);
     HY3D_LAUNCH_CHECK(ctx);
   }

@@ -152,6 +152,14 @@ __global__ void k_fill_f32(float* __restrict__ p, long long n, float v) {
   for (; t < n; t += stride) p[t] = v;
 }
 
+__global__ void k_scatter_f32(const int32_t* __restrict__ index, const float* __restrict__ vals, long long n,
+                              float* __restrict__ grid) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  int i = index[t];
+  if (i >= 0) grid[i] = vals[t];
+}
+
 __global__ void k_sentinel_nan(float* __restrict__ p, long long n, float sentinel) {
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long stride = (long long)gridDim.x * blockDim.x;
@@ -181,20 +189,25 @@ int hy3d_refine_level(hy3d_ctx* ctx, const float* d_coarse, int32_t n, float mc_
   uint32_t* words = ctx->scratch2.as<uint32_t>();
   int* blockcnt = reinterpret_cast<int*>(words + ((nwords + 63) / 64 * 64));
   long long* blockoff = reinterpret_cast<long long*>(blockcnt + ((nblocks + 63) / 64 * 64));
+  HY3D_PROF(ctx, FAM_OCTREE);
   k_coarse_active<<<(unsigned)ceil_div64(nc, 256), 256, 0, ctx->stream>>>(d_coarse, n, mc_level, act);
   HY3D_LAUNCH_CHECK(ctx);
   const uint8_t* mask = act;
   if (!last_level) {
+    HY3D_PROF(ctx, FAM_OCTREE);
     k_dilate3<<<(unsigned)ceil_div64(nc, 256), 256, 0, ctx->stream>>>(act, n, act2);
     HY3D_LAUNCH_CHECK(ctx);
     mask = act2;
   }
   const int reach = last_level ? 2 : 1;
+  HY3D_PROF(ctx, FAM_OCTREE);
   k_fine_ballot<<<nblocks, FB_WARPS * 32, 0, ctx->stream>>>(mask, n, nf, reach, words, blockcnt);
   HY3D_LAUNCH_CHECK(ctx);
+  HY3D_PROF(ctx, FAM_OCTREE);
   k_scan_i32<<<1, 1024, 0, ctx->stream>>>(blockcnt, nblocks, blockoff);
   HY3D_LAUNCH_CHECK(ctx);
   if (cap > 0) {
+    HY3D_PROF(ctx, FAM_OCTREE);
     k_fine_emit<<<nblocks, FB_WARPS * 32, 0, ctx->stream>>>(words, nwords, blockoff, d_index, cap);
     HY3D_LAUNCH_CHECK(ctx);
   }
@@ -211,6 +224,16 @@ int hy3d_fill(hy3d_ctx* ctx, float* d_grid, int64_t n, float value) {
   HY3D_CUDA(ctx, cudaSetDevice(ctx->device));
   int blocks = (int)(ceil_div64(n, 256) < (long long)ctx->num_sms * 16 ? ceil_div64(n, 256) : (long long)ctx->num_sms * 16);
   k_fill_f32<<<blocks, 256, 0, ctx->stream>>>(d_grid, n, value);
+  HY3D_LAUNCH_CHECK(ctx);
+  return HY3D_OK;
+}
+
+int hy3d_scatter(hy3d_ctx* ctx, const int32_t* d_index, const float* d_values, int64_t n, float* d_grid) {
+  if (!ctx || n < 0 || (n > 0 && (!d_index || !d_values || !d_grid))) return HY3D_ERR_ARG;
+  if (n == 0) return HY3D_OK;
+  HY3D_CUDA(ctx, cudaSetDevice(ctx->device));
+  HY3D_PROF(ctx, FAM_OCTREE);
+  k_scatter_f32<<<(unsigned)ceil_div64(n, 256), 256, 0, ctx->stream>>>(d_index, d_values, n, d_grid);
   HY3D_LAUNCH_CHECK(ctx);
   return HY3D_OK;
 }

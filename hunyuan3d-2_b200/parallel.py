@@ -1,0 +1,168 @@
+"""Multi-GPU sharding of the volume decoders: one process per GPU, ``torch.distributed``
+(NCCL over NVLink; gloo in the CPU tests) for the plumbing.
+
+The reference has no multi-device path.  Query points are independent given the
+K/V of the latent, so the grid is partitioned into slabs along axis 0 (the slowest-varying,
+contiguous one) and the ordered active list of a refined level into equal contiguous ranges.
+Exchange steps (the only collectives):
+  * dense / level-0 slabs  -> all ranks (all_gather of equal padded slabs) or -> rank 0 (gather);
+  * refined-level values   -> all ranks (all_gather of equal padded value ranges);
+  * latents are replicated by the caller (each rank receives the same ``latents``; use
+    ``broadcast_latents`` when only rank 0 holds them).
+Marching cubes then runs on rank 0 over the assembled grid: at 385^3 the grid is 228 MB
+(~0.3 ms over NVLink) and the extraction itself ~0.1 ms, far below one decoder tile of work.
+
+The communication helpers take any decode callables, so the host logic is testable on CPU with
+gloo and a fake field (tests/test_parallel_gloo.py).
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .volume_decoders import (SENTINEL, axis_tables, bind, hierarchy_levels, normalize_bounds, refine_level)
+
+
+def slab_planes(n_planes: int, rank: int, world: int) -> Tuple[int, int]:
+    """Planes [x0, x1) of an axis-0 partition into ``world`` near-equal slabs."""
+    base, rem = divmod(n_planes, world)
+    x0 = rank * base + min(rank, rem)
+    return x0, x0 + base + (1 if rank < rem else 0)
+
+
+def list_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous share [a, b) of an ordered list of n queries."""
+    return slab_planes(n, rank, world)
+
+
+def broadcast_latents(latents: Optional[torch.Tensor], shape, device, group=None, src: int = 0) -> torch.Tensor:
+    if latents is None:
+        latents = torch.empty(shape, dtype=torch.float32, device=device)
+    latents = latents.contiguous()
+    dist.broadcast(latents, src=src, group=group)
+    return latents
+
+
+def all_gather_ranges(local: torch.Tensor, counts: List[int], group=None) -> torch.Tensor:
+    """Concatenate per-rank 1-D tensors of (known) different lengths on every rank: equal padded
+    chunks through one all_gather, then trimmed."""
+    world = dist.get_world_size(group)
+    pad = max(counts) if counts else 0
+    buf = torch.zeros(pad, dtype=local.dtype, device=local.device)
+    buf[: local.numel()] = local
+    out = torch.empty(world * pad, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, buf, group=group) if hasattr(dist, "all_gather_into_tensor") and local.is_cuda \
+        else dist.all_gather(list(out.view(world, pad).unbind(0)), buf, group=group)
+    return torch.cat([out[r * pad: r * pad + counts[r]] for r in range(world)])
+
+
+def decode_dense_sharded(decode_range: Callable[[int, int, torch.Tensor], None], N: Tuple[int, int, int], device,
+                         group=None, to_all: bool = True) -> Optional[torch.Tensor]:
+    """``decode_range(first, count, out)`` fills ``out[:count]`` with the logits of flat indices
+    [first, first+count).  Every rank decodes its slab; returns the full [n0,n1,n2] grid on every
+    rank (to_all) or on rank 0 only (others get None)."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    n0, n1, n2 = N
+    plane = n1 * n2
+    x0, x1 = slab_planes(n0, rank, world)
+    local = torch.empty((x1 - x0) * plane, dtype=torch.float32, device=device)
+    if x1 > x0:
+        decode_range(x0 * plane, (x1 - x0) * plane, local)
+    counts = [(b - a) * plane for a, b in (slab_planes(n0, r, world) for r in range(world))]
+    if to_all:
+        return all_gather_ranges(local, counts, group).view(n0, n1, n2)
+    if rank == 0:
+        grid = torch.empty(n0 * plane, dtype=torch.float32, device=device)
+        grid[: counts[0]] = local
+        reqs, off = [], counts[0]
+        for r in range(1, world):
+            if counts[r]:
+                reqs.append(dist.irecv(grid[off: off + counts[r]], src=r, group=group))
+            off += counts[r]
+        for q in reqs:
+            q.wait()
+        return grid.view(n0, n1, n2)
+    if local.numel():
+        dist.send(local, dst=0, group=group)
+    return None
+
+
+def decode_list_sharded(decode_values: Callable[[torch.Tensor], torch.Tensor], index: torch.Tensor, group=None) -> torch.Tensor:
+    """``decode_values(index_slice) -> logits`` for an ordered index list known identically on all
+    ranks; each rank evaluates its contiguous share, the values are all-gathered."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    n = index.numel()
+    a, b = list_range(n, rank, world)
+    vals = decode_values(index[a:b]) if b > a else torch.empty(0, dtype=torch.float32, device=index.device)
+    counts = [hi - lo for lo, hi in (list_range(n, r, world) for r in range(world))]
+    return all_gather_ranges(vals, counts, group)
+
+
+class ShardedVanillaVolumeDecoder:
+    """VanillaVolumeDecoder (reference volume_decoders.py:141-182) over a process group; same
+    call signature.  Returns the grid on rank 0 (float32 [B,N,N,N]) and None on the other ranks."""
+
+    def __init__(self, group=None):
+        self.group = group
+
+    @torch.no_grad()
+    def __call__(self, latents, geo_decoder, bounds=1.01, num_chunks=10000, octree_resolution=None, enable_pbar=True,
+                 **kwargs):
+        ctx = bind(latents, geo_decoder)
+        axes = axis_tables(bounds, octree_resolution)
+        N = int(octree_resolution) + 1
+        outs = []
+        for b in range(latents.shape[0]):
+            ctx.prepare_kv(latents[b])
+            g = decode_dense_sharded(lambda first, count, out: ctx.decode_dense(axes, first, count, out), (N, N, N),
+                                     latents.device, self.group, to_all=False)
+            outs.append(g)
+        if dist.get_rank(self.group) != 0:
+            return None
+        return torch.stack(outs, 0)
+
+
+class ShardedHierarchicalVolumeDecoding:
+    """HierarchicalVolumeDecoding (reference :185-277, patched coordinates) over a process group.
+    Every rank ends with the full grid (the next level's active set is recomputed identically
+    everywhere from it); returns it on all ranks."""
+
+    def __init__(self, group=None):
+        self.group = group
+
+    @torch.no_grad()
+    def __call__(self, latents, geo_decoder, bounds=1.01, num_chunks=10000, mc_level=0.0, octree_resolution=None,
+                 min_resolution=63, enable_pbar=True, **kwargs):
+        ctx = bind(latents, geo_decoder)
+        levels = hierarchy_levels(octree_resolution, min_resolution)
+        b6 = normalize_bounds(bounds)
+        bbox_min, bbox_size = b6[:3], b6[3:] - b6[:3]
+        outs = []
+        self.last_stats = []
+        for b in range(latents.shape[0]):
+            ctx.prepare_kv(latents[b])
+            n0 = levels[0] + 1
+            ax = axis_tables(bounds, levels[0])
+            grid = decode_dense_sharded(lambda first, count, out: ctx.decode_dense(ax, first, count, out), (n0, n0, n0),
+                                        latents.device, self.group, to_all=True).contiguous()
+            queries = [n0 ** 3]
+            for r in levels[1:]:
+                index = refine_level(ctx, grid, mc_level, last=(r == levels[-1]))
+                n = r + 1
+                cell = (bbox_size / r).astype(np.float32)
+
+                def values(idx):
+                    return ctx.decode_list_values(idx, (n, n, n), cell, bbox_min.astype(np.float32))
+                vals = decode_list_sharded(values, index, self.group)
+                nxt = torch.empty((n, n, n), dtype=torch.float32, device=latents.device)
+                ctx.fill(nxt, SENTINEL)
+                ctx.scatter(index, vals, nxt)
+                grid = nxt
+                queries.append(int(index.numel()))
+            ctx.sentinel_to_nan(grid, SENTINEL)
+            outs.append(grid)
+            self.last_stats.append({"levels": levels, "queries": queries})
+        return torch.stack(outs, 0).to(latents.dtype)

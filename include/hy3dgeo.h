@@ -98,6 +98,13 @@ int hy3d_decode_dense(hy3d_ctx* ctx, const float* h_axis0, const float* h_axis1,
 int hy3d_decode_list(hy3d_ctx* ctx, const int32_t* d_index, int64_t n, int32_t n0, int32_t n1, int32_t n2,
                      const float h_cell[3], const float h_bmin[3], float* d_grid);
 
+/* Same queries as hy3d_decode_list, compact result: d_values[q] = logit of d_index[q] (used when
+ * the ordered list is split across ranks and the values are all-gathered before the scatter). */
+int hy3d_decode_list_values(hy3d_ctx* ctx, const int32_t* d_index, int64_t n, int32_t n0, int32_t n1, int32_t n2,
+                            const float h_cell[3], const float h_bmin[3], float* d_values);
+/* d_grid[d_index[q]] = d_values[q] (reference: next_logits[nidx] = grid_logits, volume_decoders.py:273). */
+int hy3d_scatter(hy3d_ctx* ctx, const int32_t* d_index, const float* d_values, int64_t n, float* d_grid);
+
 /* ---- octree refinement: replaces volume_decoders.py:29-119 and :245-260 / :376-391 ----- */
 /* Active fine voxels of one coarse->fine step: near-surface | band mask,
  * dilation, x2 up-sampling, dilation, ordered compaction.  d_coarse: fp32 [n,n,n] (sentinel
@@ -127,6 +134,15 @@ int hy3d_mc_emit(hy3d_ctx* ctx, const double h_div[3], const double h_mul[3], co
 /* Table-independent classification for parity tests: 8-bit case per cube, [n0-1,n1-1,n2-1]. */
 int hy3d_mc_cases(hy3d_ctx* ctx, const float* d_grid, int32_t n0, int32_t n1, int32_t n2, float level,
                   uint8_t* d_cases);
+
+/* ---- measurement ----------------------------------------------------------------------- */
+/* Device timing per kernel family with CUDA events recorded on the launch stream around every
+ * launch (enable=1).  hy3d_profile_read synchronises, returns and clears the totals:
+ * h_ms[f] milliseconds and h_count[f] launches of family f.  Families: 0 embed, 1 gemm query_proj,
+ * 2 layernorm, 3 gemm c_q, 4 attention, 5 gemm c_proj, 6 gemm c_fc, 7 gemm mlp.c_proj, 8 head,
+ * 9 mc bits, 10 mc rowcount, 11 mc scan, 12 mc emit, 13 octree, 14 kv prepare, 15 kv select. */
+int hy3d_profile(hy3d_ctx* ctx, int enable);
+int hy3d_profile_read(hy3d_ctx* ctx, double h_ms[16], int64_t h_count[16]);
 
 /* ---- diagnostics ---------------------------------------------------------------------- */
 /* Synchronises the stream and returns + clears the tensor-path watchdog record:

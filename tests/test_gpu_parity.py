@@ -1,0 +1,291 @@
+"""GPU parity tests (pytest -m gpu, run on a B200): the CUDA path through the C-ABI against the
+oracle on the same seeded inputs, against the committed golden vectors from the real reference,
+and — at BASELINE sizes — through size-independent properties.
+
+Tolerances (north_star): logits within 1e-3 abs of the fp32 reference for the O(1)-scale field;
+bit-exact cube classification, active-cell sets and face indexing given the same field; Chamfer
+distance < 1e-4 of the bbox diagonal.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import hy3dgeo
+from hy3dgeo import _lib, weights as W
+from hy3dgeo.surface_extractors import MCSurfaceExtractor
+from hy3dgeo.volume_decoders import HierarchicalVolumeDecoding, VanillaVolumeDecoder, bind
+from oracle import decoder as OD, mc as OM, volume as OV
+
+pytestmark = pytest.mark.gpu
+CFG = {"mini": W.MINI, "full": W.FULL, "turbo": W.MINI_TURBO}
+LOGIT_TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def ctx(dev):
+    return _lib.get_context(dev)
+
+
+def sphere(n, r=0.6, sharp=20.0):
+    x = np.linspace(-1.01, 1.01, n, dtype=np.float32)
+    X, Y, Z = np.meshgrid(x, x, x, indexing="ij")
+    return np.tanh(sharp * (r - np.sqrt(X * X + Y * Y + Z * Z))).astype(np.float32)
+
+
+def gpu_mc(ctx, vol, level, div=(1, 1, 1), mul=(1, 1, 1), add=(0, 0, 0)):
+    g = torch.from_numpy(np.ascontiguousarray(vol)).cuda()
+    nv, nf, mm = ctx.mc_count(g, level)
+    v = torch.empty((nv, 3), dtype=torch.float32, device="cuda")
+    f = torch.empty((nf, 3), dtype=torch.int32, device="cuda")
+    ctx.mc_emit(div, mul, add, v, f)
+    return v.cpu().numpy(), f.cpu().numpy(), mm
+
+
+def oracle_mc_raw(vol, level):
+    import ctypes
+    lib = OM._load()
+    pv, pf, nv, nf = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_int64(), ctypes.c_int64()
+    vol = np.ascontiguousarray(vol, np.float32)
+    lib.hy3d_oracle_mc(vol.ctypes.data, *vol.shape, float(level), ctypes.byref(pv), ctypes.byref(nv), ctypes.byref(pf), ctypes.byref(nf))
+    V, Fc = nv.value, nf.value
+    verts = np.ctypeslib.as_array(ctypes.cast(pv, ctypes.POINTER(ctypes.c_float)), shape=(max(V, 1), 3))[:V].copy()
+    faces = np.ctypeslib.as_array(ctypes.cast(pf, ctypes.POINTER(ctypes.c_int32)), shape=(max(Fc, 1), 3))[:Fc].copy()
+    lib.hy3d_oracle_free(pv); lib.hy3d_oracle_free(pf)
+    return verts, faces
+
+
+def bits_equal(a, b):
+    return a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+# ------------------------------------------------------------------------------ marching cubes
+@pytest.mark.parametrize("shape,level", [((2, 2, 2), 0.0), ((3, 5, 33), 0.1), ((17, 9, 32), 0.0), ((9, 31, 65), -0.2),
+                                         ((20, 21, 97), 0.0)])
+def test_mc_random_fields_bit_exact(ctx, shape, level):
+    rng = np.random.default_rng(sum(shape))
+    vol = rng.standard_normal(shape).astype(np.float32)
+    assert np.array_equal(ctx.mc_cases(torch.from_numpy(vol).cuda(), level).cpu().numpy(), OM.cube_cases(vol, level))
+    v, f, _ = gpu_mc(ctx, vol, level)
+    vo, fo = oracle_mc_raw(vol, level)
+    assert bits_equal(v, vo) and np.array_equal(f, fo)
+
+
+def test_mc_sphere_nan_and_exact_zero(ctx):
+    vol = sphere(65)
+    vol[10, 10, 10] = 0.0                                   # exact level value: "v - level > 0" is false
+    v, f, mm = gpu_mc(ctx, vol, 0.0)
+    vo, fo = oracle_mc_raw(vol, 0.0)
+    assert bits_equal(v, vo) and np.array_equal(f, fo) and f.shape[0] == 2 * v.shape[0] - 4
+    assert mm[0] == vol.min() and mm[1] == vol.max() and mm[2] is False
+    nanv = vol.copy()
+    nanv[np.abs(nanv) > 0.999] = np.nan                     # unvisited voxels of the sparse decoders
+    v, f, mm = gpu_mc(ctx, nanv, 0.0)
+    vo, fo = oracle_mc_raw(nanv, 0.0)
+    assert bits_equal(v, vo) and np.array_equal(f, fo) and mm[2] is True and np.isnan(v).any()
+
+
+def test_mc_extractor_contract(dev):
+    """MCSurfaceExtractor.run/__call__ vs the restated reference call (surface_extractors.py:50-76):
+    float64 rescale by res+1 (also when the grid is smaller than res+1, FlashVDM), dtypes, None on error."""
+    ext = MCSurfaceExtractor()
+    vol = sphere(61)
+    for res, bounds in [(60, 1.01), (64, 1.01), (60, [-1.0, -0.5, -2.0, 1.0, 1.5, 2.0])]:
+        v, f = ext.run(torch.from_numpy(vol).to(dev), mc_level=0.0, bounds=bounds, octree_resolution=res)
+        vo, fo = OM.mc_surface_extract(vol, mc_level=0.0, bounds=bounds, octree_resolution=res)
+        assert v.dtype == np.float32 and f.dtype == np.int32 and f.flags["C_CONTIGUOUS"]
+        assert bits_equal(v, vo) and np.array_equal(f, fo)
+    batch = torch.from_numpy(np.stack([vol, np.full_like(vol, -1.0)])).to(dev)
+    outs = ext(batch, mc_level=0.0, bounds=1.01, octree_resolution=60, mc_algo="mc", num_chunks=8000, enable_pbar=False)
+    assert outs[0] is not None and outs[1] is None            # level outside the data range -> item is None
+    with pytest.raises(ValueError):
+        ext.run(batch[1], mc_level=0.0, bounds=1.01, octree_resolution=60)
+    half = torch.from_numpy(vol).to(dev).half()               # fp16 grids (reference GPU dtype) are accepted
+    v16, f16 = ext.run(half, mc_level=0.0, bounds=1.01, octree_resolution=60)
+    assert f16.shape[0] > 0
+
+
+@pytest.mark.parametrize("n", [257, 385])
+def test_mc_full_size_properties(ctx, n):
+    """BASELINE grid sizes: V == number of sign-change grid edges, closed genus-0 surface F == 2V-4,
+    every face index valid, vertices on the analytic sphere."""
+    x = torch.linspace(-1.01, 1.01, n, device="cuda")
+    r = torch.sqrt(x[:, None, None] ** 2 + x[None, :, None] ** 2 + x[None, None, :] ** 2)
+    g = torch.tanh(20 * (0.6 - r)).contiguous()
+    ins = g > 0
+    edges = int((ins[1:] != ins[:-1]).sum() + (ins[:, 1:] != ins[:, :-1]).sum() + (ins[:, :, 1:] != ins[:, :, :-1]).sum())
+    nv, nf, mm = ctx.mc_count(g, 0.0)
+    assert nv == edges and nf == 2 * nv - 4
+    v = torch.empty((nv, 3), dtype=torch.float32, device="cuda")
+    f = torch.empty((nf, 3), dtype=torch.int32, device="cuda")
+    ctx.mc_emit([n - 1] * 3, [2.02] * 3, [-1.01] * 3, v, f)
+    assert int(f.min()) == 0 and int(f.max()) == nv - 1
+    assert float((v.norm(dim=1) - 0.6).abs().max()) < 2.02 / (n - 1) * 0.05
+    e = torch.cat([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]]).long()
+    key = torch.minimum(e[:, 0], e[:, 1]) * nv + torch.maximum(e[:, 0], e[:, 1])
+    _, cnt = torch.unique(key, return_counts=True)
+    assert bool((cnt == 2).all())                                # watertight
+
+
+# ------------------------------------------------------------------------------------- octree
+def test_refine_matches_oracle(ctx):
+    rng = np.random.default_rng(3)
+    base = sphere(33)
+    holes = base.copy(); holes[rng.random(base.shape) < 0.3] = -10000.0
+    noise = (rng.standard_normal((17, 17, 17)) * 2).astype(np.float32)
+    zeros = base.copy(); zeros[rng.random(base.shape) < 0.05] = 0.0
+    for grid in (base, holes, noise, zeros):
+        for level in (0.0, 0.25):
+            for last in (False, True):
+                want = np.flatnonzero(OV.refine_active_set(grid, level, last).reshape(-1))
+                idx = torch.empty(max(2 * want.size, 8), dtype=torch.int32, device="cuda")
+                cnt = ctx.refine_level(torch.from_numpy(grid).cuda(), level, last, idx)
+                assert cnt == want.size and np.array_equal(idx[:cnt].cpu().numpy(), want)
+                assert ctx.refine_level(torch.from_numpy(grid).cuda(), level, last, None) == want.size     # count-only call
+
+
+def test_refine_counts_match_reference_goldens(ctx, gold):
+    """Visited-set sizes produced by the reference itself at octree 128:
+    Hierarchical 65^3 -> 129^3: 294 426;  FlashVDM 64^3 -> 127^3: 286 014."""
+    g = gold("volume_analytic.npz")
+    for n, key in [(65, "hier128_visited"), (64, "flash128_visited")]:
+        coarse = torch.from_numpy(OV.vanilla_decode(lambda p: torch.tanh(20 * (0.6 - p.norm(dim=-1))), 1.01, 10 ** 7, n - 1)).cuda()
+        assert ctx.refine_level(coarse, 0.0, True, None) == int(g[key])
+
+
+def test_fill_scatter_nan(ctx):
+    g = torch.empty(1000, device="cuda")
+    ctx.fill(g, -10000.0)
+    idx = torch.tensor([5, -1, 999, 17], dtype=torch.int32, device="cuda")
+    ctx.scatter(idx, torch.tensor([1.0, 2.0, 3.0, 4.0], device="cuda"), g)
+    ctx.sentinel_to_nan(g)
+    out = g.cpu().numpy()
+    assert out[5] == 1 and out[999] == 3 and out[17] == 4 and np.isnan(out).sum() == 997
+
+
+# ------------------------------------------------------------------------------------ decoder
+@pytest.mark.parametrize("tag", ["mini", "turbo", "full"])
+def test_decoder_matches_reference_golden(tag, gold, dev, ctx):
+    cfg = CFG[tag]
+    g = gold(f"decoder_{tag}.npz")
+    sd = W.synthetic_state_dict(cfg, seed=0)
+    vae = hy3dgeo.B200ShapeVAE(cfg, sd, device=dev)
+    lat = vae(W.synthetic_latents(cfg, 1, 1234).to(dev))
+    assert np.abs(lat[0, ::8].cpu().numpy() - g["latents_out_rows"]).max() < 1e-3          # ShapeVAE.forward
+    c = bind(lat, vae.geo_decoder)
+    c.prepare_kv(lat[0])
+    q = torch.from_numpy(g["queries"][0]).to(dev)
+    for prec, tol in [(_lib.PRECISION_FP32_SIMT, 3e-5), (_lib.PRECISION_FP16_TC, LOGIT_TOL)]:
+        c.set_precision(prec)
+        out = c.decode_points(q).cpu().numpy()
+        c.check_watchdog()
+        assert np.abs(out - g["logits"]).max() < tol, (tag, prec, np.abs(out - g["logits"]).max())
+    c.set_precision(_lib.PRECISION_FP16_TC)
+
+
+def test_decoder_ragged_sizes_and_chunks(dev, ctx):
+    """Empty, 1, non-multiples of the 128-row tile, and more than one 131072-point chunk."""
+    cfg = W.MINI
+    sd = W.synthetic_state_dict(cfg, seed=0, with_transformer=False)
+    gd = hy3dgeo.GeoDecoder(W.geo_decoder_state(sd), cfg)
+    lat = torch.randn(1, 512, 1024, generator=torch.Generator().manual_seed(3)).to(dev)
+    c = bind(lat, gd)
+    c.prepare_kv(lat[0])
+    gsd, fr = W.geo_decoder_state(sd), W.fourier_frequencies(cfg)
+    assert c.decode_points(torch.empty(0, 3, device=dev)).numel() == 0
+    pts = (torch.rand(131072 + 129, 3, generator=torch.Generator().manual_seed(4)) * 2 - 1) * 1.01
+    out = c.decode_points(pts.to(dev)).cpu()
+    c.check_watchdog()
+    for sl in (slice(0, 1), slice(127, 130), slice(131071, 131072 + 129)):
+        ref = OD.geo_decoder_forward(gsd, pts[None, sl], lat.cpu(), fr, cfg.dec_heads)[0, :, 0]
+        assert float((out[sl] - ref).abs().max()) < LOGIT_TOL
+    one = c.decode_points(pts[:1].to(dev)).cpu()
+    assert float((one - out[:1]).abs().max()) < 1e-6               # result independent of batch composition
+    pad = torch.randn(1, 300, 1024, generator=torch.Generator().manual_seed(5)).to(dev)   # token count not a multiple of 128
+    c.prepare_kv(pad[0])
+    o2 = c.decode_points(pts[:200].to(dev)).cpu()
+    ref = OD.geo_decoder_forward(gsd, pts[None, :200], pad.cpu(), fr, cfg.dec_heads)[0, :, 0]
+    assert float((o2 - ref).abs().max()) < LOGIT_TOL
+
+
+# ---------------------------------------------------------------------------- volume decoders
+def test_vanilla_grid_layout_and_values(dev):
+    cfg = W.MINI
+    sd = W.synthetic_state_dict(cfg, seed=0)
+    vae = hy3dgeo.B200ShapeVAE(cfg, sd, device=dev)
+    z = W.synthetic_latents(cfg, 2, 1234)
+    lat_o = OD.shapevae_forward(sd, z, cfg.heads)
+    bounds = [-1.0, -0.8, -0.6, 0.9, 1.0, 1.01]
+    grid = VanillaVolumeDecoder()(lat_o.to(dev), vae.geo_decoder, bounds=bounds, num_chunks=777, octree_resolution=12,
+                                  enable_pbar=False, some_unknown_kwarg=1)
+    assert grid.shape == (2, 13, 13, 13) and grid.dtype == torch.float32
+    gsd, fr = W.geo_decoder_state(sd), W.fourier_frequencies(cfg)
+    for b in range(2):
+        ref = OV.vanilla_decode(lambda p: OD.geo_decoder_forward(gsd, p[None], lat_o[b:b + 1], fr, cfg.dec_heads)[0, :, 0],
+                                bounds, 5000, 12)
+        assert np.abs(grid[b].cpu().numpy() - ref).max() < LOGIT_TOL
+
+
+def test_hierarchical_matches_patched_reference(gold, dev, ctx, checksum):
+    cfg = W.MINI
+    g = gold("volume_decoder_mini.npz")
+    gain = float(g["gain"])
+    sd = W.sparsify_field(W.synthetic_state_dict(cfg, seed=0), cfg, int(g["keep_freqs"]), gain, float(g["bias"]))
+    assert checksum(sd) == pytest.approx(float(g["weight_checksum"]), rel=1e-9)
+    vae = hy3dgeo.B200ShapeVAE(cfg, sd, device=dev)
+    lat = vae(W.synthetic_latents(cfg, 1, 1234).to(dev))
+    ref = g["hier32"]
+    for prec, tol in [(_lib.PRECISION_FP32_SIMT, 1e-4), (_lib.PRECISION_FP16_TC, LOGIT_TOL * gain)]:   # error scales with the head gain
+        ctx.set_precision(prec)
+        dec = HierarchicalVolumeDecoding()
+        out = dec(lat, vae.geo_decoder, bounds=1.01, num_chunks=3000, mc_level=0.0, octree_resolution=32, min_resolution=15,
+                  enable_pbar=False)[0].cpu().numpy()
+        assert np.array_equal(np.isnan(out), np.isnan(ref)), "visited set differs from the reference"
+        assert np.abs(np.nan_to_num(out) - np.nan_to_num(ref)).max() < tol
+        assert dec.last_stats[0]["queries"] == [17 ** 3, int((~np.isnan(ref)).sum())]
+    ctx.set_precision(_lib.PRECISION_FP16_TC)
+
+
+def chamfer(a, b):
+    a, b = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    d = torch.cdist(a, b)
+    return float(d.min(1).values.mean() + d.min(0).values.mean()) / 2
+
+
+def test_latents2mesh_end_to_end(dev, ctx):
+    """ShapeVAE.latents2mesh (reference model.py:105-110) through B200ShapeVAE vs the oracle pipeline
+    on identical weights/latents: Chamfer < 1e-4 * bbox diagonal; fp32 mode gives the identical mesh."""
+    cfg = W.MINI
+    sd = W.sparsify_field(W.synthetic_state_dict(cfg, seed=0), cfg, 2, 1.0, 0.0)
+    vae = hy3dgeo.B200ShapeVAE(cfg, sd, device=dev)
+    z = W.synthetic_latents(cfg, 1, 1234)
+    lat_o = OD.shapevae_forward(sd, z, cfg.heads)
+    gsd, fr = W.geo_decoder_state(sd), W.fourier_frequencies(cfg)
+    res = 40
+    grid_o = OV.vanilla_decode(lambda p: OD.geo_decoder_forward(gsd, p[None], lat_o, fr, cfg.dec_heads)[0, :, 0], 1.01, 8000, res)
+    vo, fo = OM.mc_surface_extract(grid_o, mc_level=0.0, bounds=1.01, octree_resolution=res)
+    kw = dict(bounds=1.01, mc_level=0.0, num_chunks=8000, octree_resolution=res, mc_algo="mc", enable_pbar=False)
+    diag = 2.02 * np.sqrt(3)
+    for prec in (_lib.PRECISION_FP32_SIMT, _lib.PRECISION_FP16_TC):
+        ctx.set_precision(prec)
+        out = vae.latents2mesh(vae(z.to(dev)), **kw)[0]
+        assert out is not None and out.mesh_v.dtype == np.float32 and out.mesh_f.dtype == np.int32
+        assert chamfer(out.mesh_v, vo) < 1e-4 * diag
+        if prec == _lib.PRECISION_FP32_SIMT and out.mesh_f.shape == fo.shape:
+            assert np.array_equal(out.mesh_f, fo)
+    ctx.set_precision(_lib.PRECISION_FP16_TC)
+    vae.enable_flashvdm_decoder(enabled=False)
+    assert type(vae.volume_decoder).__name__ == "VanillaVolumeDecoder"
+    with pytest.raises(ValueError):
+        vae.enable_flashvdm_decoder(mc_algo="nope")
+
+
+def test_smoke_entry():
+    import __graft_entry__ as g
+    g.smoke()
