@@ -51,7 +51,17 @@ struct GemmTC {
   const float* qn_w; const float* qn_b; int qk_norm; float qscale;   // EPI_Q
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+// exact-erf GELU (reference attention_blocks.py:177) without erff's two divergent branches:
+// 1 - erf(t) = 2^(-t g(t)), g a degree-5 minimax fit on [0,4] (tools fit: |erf err| < 3e-7,
+// |gelu err| < 7e-7 in fp32 — far below the fp16 rounding of the stored activation).
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float t = fminf(fabsf(x) * 0.70710678118654752440f, 4.0f);
+  float g = -1.588800078e-04f;
+  g = fmaf(g, t, 3.746585688e-03f); g = fmaf(g, t, -3.103881516e-02f); g = fmaf(g, t, 1.498060673e-01f);
+  g = fmaf(g, t, 9.181324244e-01f); g = fmaf(g, t, 1.627928257e+00f);
+  const float e = ex2(-t * g);                   // erfc(|x|/sqrt2)
+  return 0.5f * x * (x > 0.f ? 2.f - e : e);
+}
 
 __device__ __forceinline__ void store_t16_chunk(uint8_t* tile, int r, int c16, const float* v) {
   uint4 u;
@@ -222,8 +232,8 @@ constexpr size_t GEMM_SMEM = 1024 + GEMM_STAGES * (TILE_BYTES + BTILE_BYTES) + 2
 // ------------------------------------------------------------------------------------------
 // Attention: per CTA one 128-query tile, two heads in flight (softmax warpgroup per head).
 // ------------------------------------------------------------------------------------------
-constexpr int ATT_THREADS = 384;           // warp0 producer, warp1 mma, warp2 tmem, warp3 idle, WG1 head a, WG2 head b
-constexpr int ATT_SLOTS = 6;               // K / V^T ring, 16 KB each
+constexpr int ATT_THREADS = 384;           // per head stream a in {0,1}: warp 2a producer, warp 2a+1 MMA issuer, warps 4+4a.. softmax
+constexpr int ATT_SLOTS = 3;               // K / V^T ring per stream, 16 KB each
 constexpr int TM_S0 = 0, TM_O0 = 256;      // TMEM columns: S[a] at a*128, O[a] at 256 + a*64
 
 struct AttnTC {
@@ -236,28 +246,37 @@ struct AttnTC {
   int Pb, H, nkv, ntok;  // nkv = tiles per (group, head); ntok = valid tokens when group_ntok == null
 };
 
+// Two fully independent head streams per CTA (own producer thread, MMA-issuing thread, softmax
+// warpgroup, K/V ring and barriers), so that neither stream's waits block the other: the tensor
+// pipe interleaves their MMAs, the SFU-bound softmax phases drift apart instead of marching in step.
+template <bool kHalfExp>
 __global__ void __launch_bounds__(ATT_THREADS, 1) k_attn_tc(AttnTC g) {
+  constexpr float kLazy = kHalfExp ? 1.f : 8.f;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                                   // [2][16 KB]
   uint8_t* sP = smem + 2 * TILE_BYTES;                  // [2][32 KB]
-  uint8_t* sKV = smem + 2 * TILE_BYTES + 2 * 2 * TILE_BYTES;   // [SLOTS][16 KB]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + ATT_SLOTS * TILE_BYTES);
+  uint8_t* sKV = smem + 2 * TILE_BYTES + 2 * 2 * TILE_BYTES;   // [2][SLOTS][16 KB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + 2 * ATT_SLOTS * TILE_BYTES);
   const uint32_t bar0 = smem_u32(bars);
-  auto KVFULL = [&](int s) { return bar0 + 8u * s; };
-  auto KVEMPTY = [&](int s) { return bar0 + 8u * (ATT_SLOTS + s); };
-  const uint32_t QFULL = bar0 + 8u * (2 * ATT_SLOTS), QEMPTY = QFULL + 8;
-  auto SFULL = [&](int a) { return QEMPTY + 8u + 8u * a; };
-  auto SEMPTY = [&](int a) { return QEMPTY + 8u + 8u * (2 + a); };
-  auto PFULL = [&](int a) { return QEMPTY + 8u + 8u * (4 + a); };
-  auto PVDONE = [&](int a) { return QEMPTY + 8u + 8u * (6 + a); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * ATT_SLOTS + 2 + 8);
+  constexpr int NB = 2 * ATT_SLOTS + 6;                 // barriers per stream
+  auto KVFULL = [&](int a, int s) { return bar0 + 8u * (a * NB + s); };
+  auto KVEMPTY = [&](int a, int s) { return bar0 + 8u * (a * NB + ATT_SLOTS + s); };
+  auto QFULL = [&](int a) { return bar0 + 8u * (a * NB + 2 * ATT_SLOTS); };
+  auto QEMPTY = [&](int a) { return bar0 + 8u * (a * NB + 2 * ATT_SLOTS + 1); };
+  auto SFULL = [&](int a) { return bar0 + 8u * (a * NB + 2 * ATT_SLOTS + 2); };
+  auto SEMPTY = [&](int a) { return bar0 + 8u * (a * NB + 2 * ATT_SLOTS + 3); };
+  auto PFULL = [&](int a) { return bar0 + 8u * (a * NB + 2 * ATT_SLOTS + 4); };
+  auto PVDONE = [&](int a) { return bar0 + 8u * (a * NB + 2 * ATT_SLOTS + 5); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NB);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < ATT_SLOTS; ++s) { mbar_init(KVFULL(s), 1); mbar_init(KVEMPTY(s), 1); }
-    mbar_init(QFULL, 1); mbar_init(QEMPTY, 1);
-    for (int a = 0; a < 2; ++a) { mbar_init(SFULL(a), 1); mbar_init(SEMPTY(a), 4); mbar_init(PFULL(a), 4); mbar_init(PVDONE(a), 1); }
+    for (int a = 0; a < 2; ++a) {
+      for (int s = 0; s < ATT_SLOTS; ++s) { mbar_init(KVFULL(a, s), 1); mbar_init(KVEMPTY(a, s), 1); }
+      mbar_init(QFULL(a), 1); mbar_init(QEMPTY(a), 1);
+      mbar_init(SFULL(a), 1); mbar_init(SEMPTY(a), 4); mbar_init(PFULL(a), 4); mbar_init(PVDONE(a), 1);
+    }
     fence_barrier_init();
   }
   if (warp == 2) { tmem_alloc(smem_u32(tmem_slot), 512); tmem_relinquish(); }
@@ -271,73 +290,73 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) k_attn_tc(AttnTC g) {
 
   if (warp < 4) {
     reg_dealloc<80>();
-    if (warp == 0 && lane == 0) {
-      // ---------------- producer: Q pair, then K0 K1 (j=0), then per j: K0 K1 (j+1), V0 V1 (j) ----------------
+    const int a = warp >> 1;                            // head stream
+    if ((warp & 1) == 0 && lane == 0) {
+      // ---------------- producer of stream a: Q, K(0), then per j: K(j+1), V(j) ----------------
       int s = 0; uint32_t ph = 0; uint32_t qph = 0;
+      uint8_t* ring = sKV + a * ATT_SLOTS * TILE_BYTES;
       auto push = [&](const uint8_t* src) {
-        mbar_wait(KVEMPTY(s), ph ^ 1);
-        mbar_arrive_expect_tx(KVFULL(s), TILE_BYTES);
-        bulk_g2s(smem_u32(sKV + s * TILE_BYTES), src, TILE_BYTES, KVFULL(s));
+        mbar_wait(KVEMPTY(a, s), ph ^ 1);
+        mbar_arrive_expect_tx(KVFULL(a, s), TILE_BYTES);
+        bulk_g2s(smem_u32(ring + s * TILE_BYTES), src, TILE_BYTES, KVFULL(a, s));
         if (++s == ATT_SLOTS) { s = 0; ph ^= 1; }
       };
       for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-        const int qt = item / HP, h0 = (item % HP) * 2;
+        const int qt = item / HP, h = (item % HP) * 2 + a;
         const int grp = g.tile_group ? g.tile_group[qt] : 0;
-        mbar_wait(QEMPTY, qph ^ 1);
-        mbar_arrive_expect_tx(QFULL, 2 * TILE_BYTES);
-        bulk_g2s(smem_u32(sQ), g.Q + ((size_t)qt * g.H + h0) * TILE_BYTES, 2 * TILE_BYTES, QFULL);   // heads h0, h0+1 adjacent
+        mbar_wait(QEMPTY(a), qph ^ 1);
+        mbar_arrive_expect_tx(QFULL(a), TILE_BYTES);
+        bulk_g2s(smem_u32(sQ + a * TILE_BYTES), g.Q + ((size_t)qt * g.H + h) * TILE_BYTES, TILE_BYTES, QFULL(a));
         qph ^= 1;
-        const uint8_t* kb[2]; const uint8_t* vb[2];
-        for (int a = 0; a < 2; ++a) {
-          kb[a] = g.K + ((size_t)grp * g.H + h0 + a) * nkv * TILE_BYTES;
-          vb[a] = g.V + ((size_t)grp * g.H + h0 + a) * nkv * TILE_BYTES;
-        }
-        push(kb[0]); push(kb[1]);
+        const uint8_t* kb = g.K + ((size_t)grp * g.H + h) * nkv * TILE_BYTES;
+        const uint8_t* vb = g.V + ((size_t)grp * g.H + h) * nkv * TILE_BYTES;
+        push(kb);
         for (int j = 0; j < nkv; ++j) {
-          if (j + 1 < nkv) { push(kb[0] + (size_t)(j + 1) * TILE_BYTES); push(kb[1] + (size_t)(j + 1) * TILE_BYTES); }
-          push(vb[0] + (size_t)j * TILE_BYTES); push(vb[1] + (size_t)j * TILE_BYTES);
+          if (j + 1 < nkv) push(kb + (size_t)(j + 1) * TILE_BYTES);
+          push(vb + (size_t)j * TILE_BYTES);
         }
       }
-    } else if (warp == 1 && lane == 0) {
-      // ---------------- MMA issuer ----------------
+    } else if ((warp & 1) == 1 && lane == 0) {
+      // ---------------- MMA issuer of stream a ----------------
       const uint32_t idesc_s = make_idesc_f16(128, 128);
       const uint32_t idesc_o = make_idesc_f16(128, 64);
       int s = 0; uint32_t ph = 0; uint32_t qph = 0;
-      uint32_t sph[2] = {0, 0}, pph[2] = {0, 0};      // phases of SEMPTY / PFULL waits
-      auto issue_s = [&](int a) {
-        mbar_wait(KVFULL(s), ph);
-        mbar_wait(SEMPTY(a), sph[a] ^ 1); sph[a] ^= 1;
+      uint32_t sph = 0, pph = 0;                        // phases of SEMPTY / PFULL waits
+      uint8_t* ring = sKV + a * ATT_SLOTS * TILE_BYTES;
+      auto issue_s = [&]() {
+        mbar_wait(KVFULL(a, s), ph);
+        mbar_wait(SEMPTY(a), sph ^ 1); sph ^= 1;
         fence_after_sync();
         const uint64_t ad = make_desc_sw128(smem_u32(sQ + a * TILE_BYTES));
-        const uint64_t bd = make_desc_sw128(smem_u32(sKV + s * TILE_BYTES));
+        const uint64_t bd = make_desc_sw128(smem_u32(ring + s * TILE_BYTES));
 #pragma unroll
         for (int k = 0; k < 4; ++k) mma_f16_ss(tmem + TM_S0 + a * 128, ad + 2 * k, bd + 2 * k, idesc_s, k != 0);
-        mma_commit(KVEMPTY(s));
+        mma_commit(KVEMPTY(a, s));
         mma_commit(SFULL(a));
         if (++s == ATT_SLOTS) { s = 0; ph ^= 1; }
       };
-      auto issue_pv = [&](int a, int j) {
-        mbar_wait(KVFULL(s), ph);
-        mbar_wait(PFULL(a), pph[a]); pph[a] ^= 1;
+      auto issue_pv = [&](int j) {
+        mbar_wait(KVFULL(a, s), ph);
+        mbar_wait(PFULL(a), pph); pph ^= 1;
         fence_after_sync();
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const uint64_t ad = make_desc_sw128(smem_u32(sP + a * 2 * TILE_BYTES + (k >> 2) * TILE_BYTES)) + 2 * (k & 3);
-          const uint64_t bd = make_desc_sw128(smem_u32(sKV + s * TILE_BYTES + (k >> 2) * (TILE_BYTES / 2))) + 2 * (k & 3);
+          const uint64_t bd = make_desc_sw128(smem_u32(ring + s * TILE_BYTES + (k >> 2) * (TILE_BYTES / 2))) + 2 * (k & 3);
           mma_f16_ss(tmem + TM_O0 + a * 64, ad, bd, idesc_o, (j | k) != 0);
         }
-        mma_commit(KVEMPTY(s));
+        mma_commit(KVEMPTY(a, s));
         mma_commit(PVDONE(a));
         if (++s == ATT_SLOTS) { s = 0; ph ^= 1; }
       };
       for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-        mbar_wait(QFULL, qph); qph ^= 1;
+        mbar_wait(QFULL(a), qph); qph ^= 1;
         fence_after_sync();
-        issue_s(0); issue_s(1);
+        issue_s();
         for (int j = 0; j < nkv; ++j) {
-          if (j + 1 < nkv) { issue_s(0); issue_s(1); }
-          else mma_commit(QEMPTY);                     // all S MMAs of this item issued: Q may be refilled once they finish
-          issue_pv(0, j); issue_pv(1, j);
+          if (j + 1 < nkv) issue_s();
+          else mma_commit(QEMPTY(a));                  // all S MMAs of this item issued: Q may be refilled once they finish
+          issue_pv(j);
         }
       }
     }
@@ -366,17 +385,23 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) k_attn_tc(AttnTC g) {
         __syncwarp();
         if (lane == 0) mbar_arrive(SEMPTY(a));
         const int valid = ntok - j * 128;              // columns >= valid are padding tokens
-        float mx = -INFINITY;
+        if (valid < 128) {                             // only the last tile of a ragged token count
 #pragma unroll
-        for (int i = 0; i < 128; ++i) {
-          float x = __uint_as_float(sv[i]);
-          if (i >= valid) { x = -INFINITY; sv[i] = __float_as_uint(x); }
-          mx = fmaxf(mx, x);
+          for (int i = 0; i < 128; ++i)
+            if (i >= valid) sv[i] = 0xff800000u;       // -inf
         }
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // 4 independent max chains (3-input FMNMX)
+#pragma unroll
+        for (int i = 0; i < 128; i += 8) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            mx4[u] = fmaxf(mx4[u], fmaxf(__uint_as_float(sv[i + 2 * u]), __uint_as_float(sv[i + 2 * u + 1])));
+        }
+        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
         bool need = false;
         float m_new = m;
         if (j == 0) { m_new = mx; }
-        else if (mx > m + 8.f) { m_new = mx; need = true; }   // lazy rescale: keep the old max while p <= 2^8
+        else if (mx > m + kLazy) { m_new = mx; need = true; }   // lazy rescale: keep the old max while p <= 2^kLazy
         if (j > 0) {
           mbar_wait(PVDONE(a), pv_ph); pv_ph ^= 1;            // P buffer free, O holds tiles < j
           fence_after_sync();
@@ -396,15 +421,38 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) k_attn_tc(AttnTC g) {
           }
         }
         m = m_new;
-        float sum = 0.f;
+        if constexpr (kHalfExp) {
+          // exp2 on packed halves: one MUFU op yields two probabilities already in the fp16 form the
+          // P tile needs (x = s - m is formed in fp32; |x| <= kLazy near the row maximum keeps the
+          // half rounding of x below the fp16 rounding of p itself).
+          float suma = 0.f, sumb = 0.f;
 #pragma unroll
-        for (int c16 = 0; c16 < 16; ++c16) {
-          float p[8];
+          for (int c16 = 0; c16 < 16; ++c16) {
+            uint32_t u[4];
+            __half2 acc = __float2half2_rn(0.f);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) { p[i] = ex2(__uint_as_float(sv[c16 * 8 + i]) - m); sum += p[i]; }
-          store_t16_chunk(sPa + (c16 >> 3) * TILE_BYTES, r, c16 & 7, p);
+            for (int i = 0; i < 4; ++i) {
+              const __half2 xh = __floats2half2_rn(__uint_as_float(sv[c16 * 8 + 2 * i]) - m, __uint_as_float(sv[c16 * 8 + 2 * i + 1]) - m);
+              const __half2 ph = ex2_h2(xh);
+              u[i] = *reinterpret_cast<const uint32_t*>(&ph);
+              acc = __hadd2(acc, ph);
+            }
+            const float2 af = __half22float2(acc);
+            suma += af.x; sumb += af.y;
+            *reinterpret_cast<uint4*>(sPa + (c16 >> 3) * TILE_BYTES + sw128_off(r, c16 & 7)) = make_uint4(u[0], u[1], u[2], u[3]);
+          }
+          l += suma + sumb;
+        } else {
+          float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int c16 = 0; c16 < 16; ++c16) {
+            float p[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { p[i] = ex2(__uint_as_float(sv[c16 * 8 + i]) - m); sum4[i & 3] += p[i]; }
+            store_t16_chunk(sPa + (c16 >> 3) * TILE_BYTES, r, c16 & 7, p);
+          }
+          l += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
         }
-        l += sum;
         fence_proxy_async_smem();
         fence_before_sync();
         __syncwarp();
@@ -434,7 +482,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) k_attn_tc(AttnTC g) {
   if (warp == 2) tmem_dealloc(tmem, 512);
 }
 
-constexpr size_t ATT_SMEM = 1024 + (2 + 4 + ATT_SLOTS) * TILE_BYTES + 512;
+constexpr size_t ATT_SMEM = 1024 + (2 + 4 + 2 * ATT_SLOTS) * TILE_BYTES + 512;
 
 // ------------------------------------------------------------------------------------------
 // Small HBM-bound stages around the GEMMs
@@ -680,7 +728,8 @@ int hy3d_decode_tc(hy3d_ctx* ctx, const QuerySource& src_in, long long n, float*
   uint8_t* ta = ctx->ws[3].as<uint8_t>();
   uint8_t* tq = ctx->ws[4].as<uint8_t>();
   uint8_t* th = ctx->ws[5].as<uint8_t>();
-  HY3D_CUDA(ctx, cudaFuncSetAttribute(k_attn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
+  HY3D_CUDA(ctx, cudaFuncSetAttribute(k_attn_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
+  HY3D_CUDA(ctx, cudaFuncSetAttribute(k_attn_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
   const float pi_mul = w.include_pi ? 3.14159265358979323846f : 1.f;
   for (long long p0 = 0; p0 < n; p0 += CH) {
     const long long P = (n - p0 < CH) ? (n - p0) : CH;
@@ -716,7 +765,8 @@ int hy3d_decode_tc(hy3d_ctx* ctx, const QuerySource& src_in, long long n, float*
       int items = Pb * (H / 2);
       int grid = items < ctx->num_sms ? items : ctx->num_sms;
       HY3D_PROF(ctx, FAM_ATTN);
-      k_attn_tc<<<grid, ATT_THREADS, ATT_SMEM, ctx->stream>>>(a);
+      if (ctx->attn_half_exp) k_attn_tc<true><<<grid, ATT_THREADS, ATT_SMEM, ctx->stream>>>(a);
+      else k_attn_tc<false><<<grid, ATT_THREADS, ATT_SMEM, ctx->stream>>>(a);
       HY3D_LAUNCH_CHECK(ctx);
     }
     if (int rc = hy3d_debug_keep(ctx, 3, ta, (size_t)Pp * W * 2, 2, Pp, W)) return rc;

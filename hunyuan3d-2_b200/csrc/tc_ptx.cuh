@@ -151,6 +151,12 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+__device__ __forceinline__ __half2 ex2_h2(__half2 x) {
+  uint32_t xi = *reinterpret_cast<uint32_t*>(&x), yi;
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(yi) : "r"(xi));
+  return *reinterpret_cast<__half2*>(&yi);
+}
+
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
