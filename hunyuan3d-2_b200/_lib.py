@@ -39,6 +39,11 @@ class DecoderDesc(C.Structure):
                  "ln_post_w", "ln_post_b", "out_w", "out_b")]
 
 
+class Coords(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("cell", C.c_float * 3), ("bmin", C.c_float * 3),
+                ("axis0", C.c_void_p), ("axis1", C.c_void_p), ("axis2", C.c_void_p)]
+
+
 # name -> (restype, argtypes): every symbol declared in include/hy3dgeo.h
 SYMBOLS = {
     "hy3d_create": (C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
@@ -57,6 +62,12 @@ SYMBOLS = {
     "hy3d_decode_list_values": (C.c_int, [C.c_void_p, c_i32p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                           C.POINTER(C.c_float), C.POINTER(C.c_float), c_f32p]),
     "hy3d_scatter": (C.c_int, [C.c_void_p, c_i32p, c_f32p, C.c_int64, c_f32p]),
+    "hy3d_flash_select": (C.c_int, [C.c_void_p, c_i32p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.POINTER(Coords),
+                                    c_i32p, C.c_int32, C.c_int32, C.c_int32]),
+    "hy3d_decode_flash": (C.c_int, [C.c_void_p, c_i32p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.POINTER(Coords),
+                                    c_i32p, c_f32p]),
+    "hy3d_flash_selection": (C.c_int, [C.c_void_p, c_i32p, C.c_int64]),
+    "hy3d_flash_group_tokens": (C.c_int, [C.c_void_p, c_i32p, C.c_int32]),
     "hy3d_refine_level": (C.c_int, [C.c_void_p, c_f32p, C.c_int32, C.c_float, C.c_int32, c_i32p, C.c_int64,
                                     C.POINTER(C.c_int64)]),
     "hy3d_fill": (C.c_int, [C.c_void_p, c_f32p, C.c_int64, C.c_float]),
@@ -270,6 +281,45 @@ class GeoContext:
         self.sync_stream()
         self._check(self.lib.hy3d_scatter(self.h, _ptr(index.contiguous()), _ptr(values.contiguous()), index.numel(),
                                           _ptr(grid)), "hy3d_scatter")
+
+    # ---- FlashVDM ---------------------------------------------------------------------------
+    @staticmethod
+    def _coords(cell=None, bmin=None, axes=None):
+        c = Coords()
+        keep = []
+        if axes is not None:
+            c.mode = 3
+            keep = [np.ascontiguousarray(a, dtype=np.float32) for a in axes]
+            c.axis0, c.axis1, c.axis2 = (a.ctypes.data for a in keep)
+        else:
+            c.mode = 2
+            c.cell = (C.c_float * 3)(*[float(v) for v in cell])
+            c.bmin = (C.c_float * 3)(*[float(v) for v in bmin])
+        return c, keep
+
+    def flash_select(self, sample_index: torch.Tensor, dims, sample_off: torch.Tensor, n_groups: int, topk: int,
+                     merge: bool, cell=None, bmin=None, axes=None):
+        self.sync_stream()
+        c, keep = self._coords(cell, bmin, axes)
+        self._check(self.lib.hy3d_flash_select(self.h, _ptr(sample_index), sample_index.numel(), dims[0], dims[1], dims[2],
+                                               C.byref(c), _ptr(sample_off), n_groups, topk, int(merge)), "hy3d_flash_select")
+
+    def decode_flash(self, index: torch.Tensor, dims, tile_group: torch.Tensor, grid: torch.Tensor, cell=None, bmin=None,
+                     axes=None):
+        self.sync_stream()
+        c, keep = self._coords(cell, bmin, axes)
+        self._check(self.lib.hy3d_decode_flash(self.h, _ptr(index), index.numel(), dims[0], dims[1], dims[2], C.byref(c),
+                                               _ptr(tile_group), _ptr(grid)), "hy3d_decode_flash")
+
+    def flash_selection(self, count: int) -> torch.Tensor:
+        out = torch.empty(count, dtype=torch.int32, device=self.device)
+        self._check(self.lib.hy3d_flash_selection(self.h, _ptr(out), count), "hy3d_flash_selection")
+        return out
+
+    def flash_group_tokens(self, n_groups: int) -> torch.Tensor:
+        out = torch.empty(n_groups, dtype=torch.int32, device=self.device)
+        self._check(self.lib.hy3d_flash_group_tokens(self.h, _ptr(out), n_groups), "hy3d_flash_group_tokens")
+        return out
 
     # ---- octree -------------------------------------------------------------------------------
     def refine_level(self, coarse: torch.Tensor, mc_level: float, last: bool, index: Optional[torch.Tensor]) -> int:

@@ -43,6 +43,7 @@ struct DecoderWeights {
   // tcgen05 operand images (decoder_tc.cu)
   DevBuf tc;
   const __half *t_qp, *t_cq, *t_cproj, *t_fc, *t_mp;      // B tiles
+  const __half* t_cq3;                                    // c_q split [W_hi | W_hi | W_lo], K = 3W (fp32-grade q for KV selection)
 };
 
 struct KVState {
@@ -51,6 +52,16 @@ struct KVState {
   int Mpad = 0;                       // tokens padded to 128
   DevBuf k32, v32;                    // fp32 [H, M, D] (after k_norm) — SIMT path + selection
   DevBuf ktile, vtile;                // fp16 UMMA tiles — tcgen05 path
+};
+
+// FlashVDM per-group K/V selection (attention_processors.py:35-96): gathered token subsets as UMMA tiles
+struct KVSelState {
+  bool ready = false;
+  int G = 0, nkv = 0;                 // groups, 128-token tiles per (group, head)
+  DevBuf ktile, vtile;                // [G][H][nkv][16 KB]
+  DevBuf ntok;                        // int [G] valid tokens per group
+  DevBuf sel;                         // int [G][H][T] (mean) or [G][Mpad] (merge) selected token ids
+  DevBuf qs, qbar, mask;              // sampled q fp32 [S, W]; group means [G, W]; merge-mode token bitmasks
 };
 
 struct McState {
@@ -83,6 +94,7 @@ struct hy3d_ctx {
   std::string err;
   DecoderWeights w;
   KVState kv;
+  KVSelState kvsel;
   McState mc;
   DevBuf ws[12];                      // decoder workspaces
   DevBuf scratch, scratch2;           // octree / misc
@@ -140,7 +152,7 @@ static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b;
 
 // ---- decoder entry points implemented per precision --------------------------------------
 struct QuerySource {
-  int mode;                 // 0 explicit xyz, 1 dense grid range, 2 index list
+  int mode;                 // 0 explicit xyz, 1 dense grid range, 2 index list (idx*cell+bmin), 3 index list (axis tables)
   const float* xyz;         // mode 0
   const float* axis;        // mode 1: device table [n0 + n1 + n2]
   const int32_t* index;     // mode 2
@@ -152,6 +164,10 @@ struct QuerySource {
 int hy3d_decode_simt(hy3d_ctx* ctx, const QuerySource& src, long long n, float* d_out, int out_mode);
 int hy3d_decode_tc(hy3d_ctx* ctx, const QuerySource& src, long long n, float* d_out, int out_mode);
 int hy3d_tc_prepare_weights(hy3d_ctx* ctx);
+// decode with per-q-tile KV groups (tile_group: device int per 128-query tile of the whole list) from ctx->kvsel
+int hy3d_decode_tc_groups(hy3d_ctx* ctx, const QuerySource& src, long long n, float* d_out, int out_mode, const int* d_tile_group);
+// q after q_norm (unscaled), ~fp32 accuracy via 3-term split fp16 tensor GEMMs: d_q row-major [ceil128(n), W]
+int hy3d_tc_sample_q(hy3d_ctx* ctx, const QuerySource& src, long long n, float* d_q);
 int hy3d_tc_prepare_kv(hy3d_ctx* ctx);
 int hy3d_simt_prepare_kv(hy3d_ctx* ctx, const float* d_latents, int M);
 
@@ -170,6 +186,7 @@ __device__ __forceinline__ void hy3d_query_point(const QuerySource& s, long long
     if (lin < 0) { x = y = z = 0.f; return; }
     int k = lin % s.n2; int t = lin / s.n2;
     int j = t % s.n1; int i = t / s.n1;
+    if (s.mode == 3) { x = s.axis[i]; y = s.axis[s.n0 + j]; z = s.axis[s.n0 + s.n1 + k]; return; }
     // volume_decoders.py:394-396: float32(idx) * float32(cell) + float32(bbox_min), no FMA contraction
     x = __fadd_rn(__fmul_rn((float)i, s.cell[0]), s.bmin[0]);
     y = __fadd_rn(__fmul_rn((float)j, s.cell[1]), s.bmin[1]);

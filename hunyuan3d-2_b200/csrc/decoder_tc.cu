@@ -38,7 +38,7 @@ constexpr int GEMM_STAGES = 4;
 constexpr int GEMM_THREADS = 384;          // warp0 producer, warp1 mma, warp2 tmem, warp3 idle, warps 4..11 epilogue
 constexpr float LOG2E = 1.4426950408889634f;
 
-enum { EPI_X0 = 0, EPI_Q = 1, EPI_RES = 2, EPI_GELU = 3 };
+enum { EPI_X0 = 0, EPI_Q = 1, EPI_RES = 2, EPI_GELU = 3, EPI_QF32 = 4 };
 
 struct GemmTC {
   const uint8_t* A;      // T16 tiles [Mb][KB]
@@ -48,6 +48,7 @@ struct GemmTC {
   const float* Rin;      // R32 (EPI_RES)
   float* Rout;           // R32 (EPI_X0, EPI_RES)
   uint8_t* Tout;         // T16 (EPI_Q, EPI_GELU)
+  float* Fout;           // row-major fp32 [P, N] (EPI_QF32)
   const float* qn_w; const float* qn_b; int qk_norm; float qscale;   // EPI_Q
 };
 
@@ -154,7 +155,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(GemmTC g) {
       fence_after_sync();
       const uint32_t trow = tmem + acc * BN + ((uint32_t)(q * 32) << 16);
       const int col0 = nb * BN + half * (BN / 2);          // first global column of this warp's half
-      if constexpr (EPI == EPI_Q) {
+      if constexpr (EPI == EPI_Q || EPI == EPI_QF32) {
 #pragma unroll 1
         for (int hh = 0; hh < 2; ++hh) {                    // two 64-column heads per half
           uint32_t v[64];
@@ -180,9 +181,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(GemmTC g) {
 #pragma unroll
             for (int i = 0; i < 64; ++i) x[i] *= g.qscale;
           }
-          uint8_t* tile = g.Tout + ((size_t)mb * (g.N / 64) + (c >> 6)) * TILE_BYTES;
+          if constexpr (EPI == EPI_QF32) {
+            float4* o = reinterpret_cast<float4*>(g.Fout + ((size_t)mb * TILE_M + r) * g.N + c);
 #pragma unroll
-          for (int c16 = 0; c16 < 8; ++c16) store_t16_chunk(tile, r, c16, x + 8 * c16);
+            for (int i4 = 0; i4 < 16; ++i4) o[i4] = make_float4(x[4 * i4], x[4 * i4 + 1], x[4 * i4 + 2], x[4 * i4 + 3]);
+          } else {
+            uint8_t* tile = g.Tout + ((size_t)mb * (g.N / 64) + (c >> 6)) * TILE_BYTES;
+#pragma unroll
+            for (int c16 = 0; c16 < 8; ++c16) store_t16_chunk(tile, r, c16, x + 8 * c16);
+          }
         }
       } else {
 #pragma unroll 1
@@ -522,6 +529,8 @@ __global__ void __launch_bounds__(128) k_embed_tc(QuerySource src, long long n, 
 }
 
 // LayerNorm over N columns: R32 -> T16 (one thread per row, one block per 128-row tile)
+// kSplit: the row is written as [hi | lo | hi] (3 * N/64 k-blocks) for the 3-term split GEMM.
+template <bool kSplit>
 __global__ void __launch_bounds__(128) k_ln_tc(const float* __restrict__ R, int N, const float* __restrict__ gam,
                                                 const float* __restrict__ bet, float eps, uint8_t* __restrict__ T) {
   const int r = threadIdx.x;
@@ -540,7 +549,8 @@ __global__ void __launch_bounds__(128) k_ln_tc(const float* __restrict__ R, int 
   const float mean = shift + ms;
   const float var = fmaxf(ss / N - ms * ms, 0.f);
   const float rstd = rsqrtf(var + eps);
-  uint8_t* tbase = T + (size_t)blockIdx.x * (N / 64) * TILE_BYTES;
+  const int KBn = N / 64;
+  uint8_t* tbase = T + (size_t)blockIdx.x * (kSplit ? 3 : 1) * KBn * TILE_BYTES;
 #pragma unroll 4
   for (int c8 = 0; c8 < N / 8; ++c8) {
     float4 v0 = __ldg(&x[(size_t)(2 * c8) * TILE_M]), v1 = __ldg(&x[(size_t)(2 * c8 + 1) * TILE_M]);
@@ -551,7 +561,16 @@ __global__ void __launch_bounds__(128) k_ln_tc(const float* __restrict__ R, int 
     o[2] = (v0.z - mean) * rstd * g0.z + b0.z; o[3] = (v0.w - mean) * rstd * g0.w + b0.w;
     o[4] = (v1.x - mean) * rstd * g1.x + b1.x; o[5] = (v1.y - mean) * rstd * g1.y + b1.y;
     o[6] = (v1.z - mean) * rstd * g1.z + b1.z; o[7] = (v1.w - mean) * rstd * g1.w + b1.w;
-    store_t16_chunk(tbase + (size_t)(c8 >> 3) * TILE_BYTES, r, c8 & 7, o);
+    if constexpr (kSplit) {
+      float hi[8], lo[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { hi[i] = __half2float(__float2half_rn(o[i])); lo[i] = o[i] - hi[i]; }
+      store_t16_chunk(tbase + (size_t)(c8 >> 3) * TILE_BYTES, r, c8 & 7, hi);
+      store_t16_chunk(tbase + (size_t)(KBn + (c8 >> 3)) * TILE_BYTES, r, c8 & 7, lo);
+      store_t16_chunk(tbase + (size_t)(2 * KBn + (c8 >> 3)) * TILE_BYTES, r, c8 & 7, hi);
+    } else {
+      store_t16_chunk(tbase + (size_t)(c8 >> 3) * TILE_BYTES, r, c8 & 7, o);
+    }
   }
 }
 
@@ -601,7 +620,8 @@ __global__ void __launch_bounds__(128) k_head_tc(const float* __restrict__ R, in
 
 // ---- operand image builders ----------------------------------------------------------------
 // fp32 row-major W[N, K] (ld = ldw) -> B16 tiles.  mode 0: plain.  mode 1: query_proj split:
-// K_out = 192 = [W_hi | W_hi | W_lo] over the first E columns (zero padded to 64).
+// K_out = 192 = [W_hi | W_hi | W_lo] over the first E columns (zero padded to 64).  mode 2: the same
+// 3-term split for a full [N, K/3] matrix.
 __global__ void k_build_b16(const float* __restrict__ Wsrc, int N, int K, int ldw, int mode, int E, uint8_t* __restrict__ out) {
   const int KB = K / 64;
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;    // one 16-byte chunk per thread
@@ -615,7 +635,12 @@ __global__ void k_build_b16(const float* __restrict__ Wsrc, int N, int K, int ld
     int k = c8 * 8 + i;
     float w;
     if (mode == 0) w = Wsrc[(size_t)n * ldw + k];
-    else {
+    else if (mode == 2) {                      // [W_hi | W_hi | W_lo], each K/3 wide
+      const int Ks = K / 3, part = k / Ks;
+      float full = Wsrc[(size_t)n * ldw + (k - part * Ks)];
+      float hi = __half2float(__float2half_rn(full));
+      w = part < 2 ? hi : full - hi;
+    } else {
       int part = k / 64, kk = k % 64;
       float full = kk < E ? Wsrc[(size_t)n * ldw + kk] : 0.f;
       float hi = __half2float(__float2half_rn(full));
@@ -678,8 +703,8 @@ int hy3d_tc_prepare_weights(hy3d_ctx* ctx) {
     return 0;
   }
   const size_t W = w.W, R = w.R;
-  const size_t n_qp = W * 192, n_cq = W * W, n_cp = W * W, n_fc = R * W * W, n_mp = R * W * W;
-  HY3D_CUDA(ctx, w.tc.reserve((n_qp + n_cq + n_cp + n_fc + n_mp) * 2));
+  const size_t n_qp = W * 192, n_cq = W * W, n_cp = W * W, n_fc = R * W * W, n_mp = R * W * W, n_cq3 = 3 * W * W;
+  HY3D_CUDA(ctx, w.tc.reserve((n_qp + n_cq + n_cp + n_fc + n_mp + n_cq3) * 2));
   __half* base = w.tc.as<__half>();
   __half* p_qp = base; __half* p_cq = p_qp + n_qp; __half* p_cp = p_cq + n_cq; __half* p_fc = p_cp + n_cp; __half* p_mp = p_fc + n_fc;
   auto build = [&](const float* src, int N, int K, int ldw, int mode, __half* dst) -> int {
@@ -693,7 +718,9 @@ int hy3d_tc_prepare_weights(hy3d_ctx* ctx) {
   if (int rc = build(w.cproj_w, (int)W, (int)W, (int)W, 0, p_cp)) return rc;
   if (int rc = build(w.fc_w, (int)(R * W), (int)W, (int)W, 0, p_fc)) return rc;
   if (int rc = build(w.mp_w, (int)W, (int)(R * W), (int)(R * W), 0, p_mp)) return rc;
-  w.t_qp = p_qp; w.t_cq = p_cq; w.t_cproj = p_cp; w.t_fc = p_fc; w.t_mp = p_mp;
+  __half* p_cq3 = p_mp + n_mp;
+  if (int rc = build(w.cq_w, (int)W, (int)(3 * W), (int)W, 2, p_cq3)) return rc;
+  w.t_qp = p_qp; w.t_cq = p_cq; w.t_cproj = p_cp; w.t_fc = p_fc; w.t_mp = p_mp; w.t_cq3 = p_cq3;
   return 0;
 }
 
@@ -713,7 +740,7 @@ int hy3d_tc_prepare_kv(hy3d_ctx* ctx) {
   return 0;
 }
 
-int hy3d_decode_tc(hy3d_ctx* ctx, const QuerySource& src_in, long long n, float* d_out, int out_mode) {
+static int decode_tc_impl(hy3d_ctx* ctx, const QuerySource& src_in, long long n, float* d_out, int out_mode, const int* d_tile_group) {
   DecoderWeights& w = ctx->w;
   if (!w.t_qp)
     return hy3d_fail(ctx, HY3D_ERR_UNSUPPORTED, "tcgen05 path needs head_dim 64 and widths that are multiples of 256");
@@ -749,7 +776,7 @@ int hy3d_decode_tc(hy3d_ctx* ctx, const QuerySource& src_in, long long n, float*
     const long long Pp = (long long)Pb * 128;
     if (int rc = hy3d_debug_keep(ctx, 0, x, (size_t)Pp * W * 4, 1, Pp, W)) return rc;
     HY3D_PROF(ctx, FAM_LN);
-    k_ln_tc<<<Pb, 128, 0, ctx->stream>>>(x, W, w.ln1_w, w.ln1_b, 1e-6f, ta);
+    k_ln_tc<false><<<Pb, 128, 0, ctx->stream>>>(x, W, w.ln1_w, w.ln1_b, 1e-6f, ta);
     HY3D_LAUNCH_CHECK(ctx);
     if (int rc = hy3d_debug_keep(ctx, 1, ta, (size_t)Pp * W * 2, 2, Pp, W)) return rc;
     // q = q_norm(c_q(ln_1 x0)) * scale * log2e
@@ -760,8 +787,13 @@ int hy3d_decode_tc(hy3d_ctx* ctx, const QuerySource& src_in, long long n, float*
     if (int rc = hy3d_debug_keep(ctx, 2, tq, (size_t)Pp * W * 2, 2, Pp, W)) return rc;
     {
       AttnTC a{};
-      a.Q = tq; a.K = ctx->kv.ktile.as<uint8_t>(); a.V = ctx->kv.vtile.as<uint8_t>(); a.O = ta;
-      a.Pb = Pb; a.H = H; a.nkv = ctx->kv.Mpad / 128; a.ntok = ctx->kv.M;
+      a.Q = tq; a.O = ta; a.Pb = Pb; a.H = H;
+      if (d_tile_group) {
+        a.K = ctx->kvsel.ktile.as<uint8_t>(); a.V = ctx->kvsel.vtile.as<uint8_t>(); a.nkv = ctx->kvsel.nkv;
+        a.tile_group = d_tile_group + p0 / 128; a.group_ntok = ctx->kvsel.ntok.as<int>();
+      } else {
+        a.K = ctx->kv.ktile.as<uint8_t>(); a.V = ctx->kv.vtile.as<uint8_t>(); a.nkv = ctx->kv.Mpad / 128; a.ntok = ctx->kv.M;
+      }
       int items = Pb * (H / 2);
       int grid = items < ctx->num_sms ? items : ctx->num_sms;
       HY3D_PROF(ctx, FAM_ATTN);
@@ -776,7 +808,7 @@ int hy3d_decode_tc(hy3d_ctx* ctx, const QuerySource& src_in, long long n, float*
     if (int rc = launch_gemm<EPI_RES>(ctx, g, FAM_GEMM_CPROJ)) return rc;
     if (int rc = hy3d_debug_keep(ctx, 4, x, (size_t)Pp * W * 4, 1, Pp, W)) return rc;
     HY3D_PROF(ctx, FAM_LN);
-    k_ln_tc<<<Pb, 128, 0, ctx->stream>>>(x, W, w.ln3_w, w.ln3_b, 1e-6f, ta);
+    k_ln_tc<false><<<Pb, 128, 0, ctx->stream>>>(x, W, w.ln3_w, w.ln3_b, 1e-6f, ta);
     HY3D_LAUNCH_CHECK(ctx);
     if (int rc = hy3d_debug_keep(ctx, 5, ta, (size_t)Pp * W * 2, 2, Pp, W)) return rc;
     // h = gelu(c_fc(ln_3 x1))
@@ -793,6 +825,52 @@ int hy3d_decode_tc(hy3d_ctx* ctx, const QuerySource& src_in, long long n, float*
     HY3D_PROF(ctx, FAM_HEAD);
     k_head_tc<<<Pb, 128, 0, ctx->stream>>>(x, W, w.ln_post ? w.lnp_w : nullptr, w.lnp_b, w.out_w, w.out_b, src, P, outp, out_mode);
     HY3D_LAUNCH_CHECK(ctx);
+  }
+  return 0;
+}
+
+int hy3d_decode_tc(hy3d_ctx* ctx, const QuerySource& src, long long n, float* d_out, int out_mode) {
+  return decode_tc_impl(ctx, src, n, d_out, out_mode, nullptr);
+}
+
+int hy3d_decode_tc_groups(hy3d_ctx* ctx, const QuerySource& src, long long n, float* d_out, int out_mode, const int* d_tile_group) {
+  if (!ctx->kvsel.ready) return hy3d_fail(ctx, HY3D_ERR_STATE, "no KV selection prepared");
+  return decode_tc_impl(ctx, src, n, d_out, out_mode, d_tile_group);
+}
+
+// Front of the chain for the sub-sampled queries that drive the FlashVDM KV selection, at ~fp32
+// accuracy: embed -> query_proj (split) -> ln_1 (split output) -> c_q (3-term split, K = 3W) -> q_norm.
+int hy3d_tc_sample_q(hy3d_ctx* ctx, const QuerySource& src_in, long long n, float* d_q) {
+  DecoderWeights& w = ctx->w;
+  if (!w.t_qp) return hy3d_fail(ctx, HY3D_ERR_UNSUPPORTED, "tcgen05 path unavailable for this decoder shape");
+  const int W = w.W;
+  const long long CH = 32768;
+  const long long chmax = n < CH ? (n + 127) / 128 * 128 : CH;
+  HY3D_CUDA(ctx, ctx->ws[7].reserve((size_t)chmax * W * 4));
+  HY3D_CUDA(ctx, ctx->ws[8].reserve((size_t)chmax * W * 2 * 3));
+  float* x = ctx->ws[7].as<float>();
+  uint8_t* ta = ctx->ws[8].as<uint8_t>();
+  const float pi_mul = w.include_pi ? 3.14159265358979323846f : 1.f;
+  for (long long p0 = 0; p0 < n; p0 += CH) {
+    const long long P = (n - p0 < CH) ? (n - p0) : CH;
+    const int Pb = (int)((P + 127) / 128);
+    QuerySource src = src_in;
+    if (src.mode == 0) src.xyz += 3 * p0;
+    else if (src.mode == 1) src.first += p0;
+    else src.index += p0;
+    HY3D_PROF(ctx, FAM_SELECT);
+    k_embed_tc<<<Pb, 128, 0, ctx->stream>>>(src, P, w.F, pi_mul, ta);
+    HY3D_LAUNCH_CHECK(ctx);
+    GemmTC g{};
+    g.Mb = Pb; g.A = ta; g.B = reinterpret_cast<const uint8_t*>(w.t_qp); g.KB = 3; g.N = W; g.Nb = W / BN; g.bias = w.qp_b; g.Rout = x;
+    if (int rc = launch_gemm<EPI_X0>(ctx, g, FAM_SELECT)) return rc;
+    HY3D_PROF(ctx, FAM_SELECT);
+    k_ln_tc<true><<<Pb, 128, 0, ctx->stream>>>(x, W, w.ln1_w, w.ln1_b, 1e-6f, ta);
+    HY3D_LAUNCH_CHECK(ctx);
+    g = GemmTC{}; g.Mb = Pb;
+    g.A = ta; g.B = reinterpret_cast<const uint8_t*>(w.t_cq3); g.KB = 3 * W / 64; g.N = W; g.Nb = W / BN; g.bias = w.cq_b;
+    g.Fout = d_q + (size_t)p0 * W; g.qn_w = w.qn_w; g.qn_b = w.qn_b; g.qk_norm = w.qk_norm ? 1 : 0; g.qscale = 1.f;
+    if (int rc = launch_gemm<EPI_QF32>(ctx, g, FAM_SELECT)) return rc;
   }
   return 0;
 }

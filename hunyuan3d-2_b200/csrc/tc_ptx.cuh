@@ -39,7 +39,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 // Watchdog: a barrier that never completes must not hang the GPU box.  On timeout the waiter records
 // {1, block, thread, barrier, parity} in hy3d_wd[] (fetch with hy3d_debug_watchdog) and every later
 // wait of the kernel gives up quickly, so the launch drains and returns (with garbage results).
-__device__ int hy3d_wd[8];
+static __device__ int hy3d_wd[8];
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 #if HY3D_TC_WATCHDOG
   uint32_t spins = 0;

@@ -105,6 +105,31 @@ int hy3d_decode_list_values(hy3d_ctx* ctx, const int32_t* d_index, int64_t n, in
 /* d_grid[d_index[q]] = d_values[q] (reference: next_logits[nidx] = grid_logits, volume_decoders.py:273). */
 int hy3d_scatter(hy3d_ctx* ctx, const int32_t* d_index, const float* d_values, int64_t n, float* d_grid);
 
+/* ---- FlashVDM: replaces FlashVDMVolumeDecoding's decoder calls (volume_decoders.py:343-371,
+ * 398-431) and the processors of attention_processors.py:35-96 ------------------------------ */
+/* How the points of an index list get their coordinates: mode 2 = float32(ijk)*cell + bmin
+ * (refined levels, volume_decoders.py:394-396), mode 3 = per-axis HOST tables (level 0 mini-grids). */
+typedef struct hy3d_coords {
+  int32_t mode;
+  float cell[3];
+  float bmin[3];
+  const float* axis0; const float* axis1; const float* axis2;
+} hy3d_coords;
+/* KV selection for G groups (mini-grids or spatial bins).  d_sample_index: flat grid indices of the
+ * sub-sampled queries (every 100th / 50th / 30th query of each group, in group order; -1 = padding),
+ * d_sample_off[g]..d_sample_off[g+1] delimits group g (DEVICE int32 [G+1]).  merge_mode 0: top-`topk`
+ * tokens per (group, head) by mean similarity; 1: union of tokens with head-averaged probability
+ * > 1e-6, shared by all heads.  The result lives in the context until the next call. */
+int hy3d_flash_select(hy3d_ctx* ctx, const int32_t* d_sample_index, int64_t n_samples, int32_t n0, int32_t n1, int32_t n2,
+                      const hy3d_coords* coords, const int32_t* d_sample_off, int32_t G, int32_t topk, int32_t merge_mode);
+/* Decode a group-ordered, 128-padded index list (-1 = padding) with the selected K/V of each
+ * tile's group (d_tile_group: DEVICE int32 [n/128]); logits scattered to d_grid[d_index[q]]. */
+int hy3d_decode_flash(hy3d_ctx* ctx, const int32_t* d_index, int64_t n, int32_t n0, int32_t n1, int32_t n2,
+                      const hy3d_coords* coords, const int32_t* d_tile_group, float* d_grid);
+/* Selected token ids / per-group token counts of the last hy3d_flash_select (parity tests). */
+int hy3d_flash_selection(hy3d_ctx* ctx, int32_t* d_out, int64_t count);
+int hy3d_flash_group_tokens(hy3d_ctx* ctx, int32_t* d_out, int32_t G);
+
 /* ---- octree refinement: replaces volume_decoders.py:29-119 and :245-260 / :376-391 ----- */
 /* Active fine voxels of one coarse->fine step: near-surface | band mask,
  * dilation, x2 up-sampling, dilation, ordered compaction.  d_coarse: fp32 [n,n,n] (sentinel
