@@ -18,7 +18,8 @@ __global__ void k_coarse_active(const float* __restrict__ g, int n, float alpha,
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)n * n * n;
   if (t >= total) return;
-  int k = t % n; long long r = t / n; int j = r % n; int i = r / n;
+  const unsigned tu = (unsigned)t;                       // grids are < 2^31 voxels: 32-bit index arithmetic
+  int k = tu % n; unsigned r = tu / n; int j = r % n; int i = r / n;
   float gv = g[t];
   float val = __fadd_rn(gv, alpha);
   bool valid = val > -9000.f;
@@ -44,7 +45,8 @@ __global__ void k_dilate3(const uint8_t* __restrict__ in, int n, uint8_t* __rest
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)n * n * n;
   if (t >= total) return;
-  int k = t % n; long long r = t / n; int j = r % n; int i = r / n;
+  const unsigned tu = (unsigned)t;
+  int k = tu % n; unsigned r = tu / n; int j = r % n; int i = r / n;
   uint8_t v = 0;
   for (int a = max(i - 1, 0); a <= min(i + 1, n - 1); ++a)
     for (int b = max(j - 1, 0); b <= min(j + 1, n - 1); ++b)
@@ -74,8 +76,11 @@ constexpr int FB_WARPS = 8;
 constexpr int FB_ITERS = 16;                      // 32-voxel words per warp
 constexpr int FB_BLOCK = FB_WARPS * FB_ITERS * 32;  // 4096 fine voxels per block
 
-__global__ void __launch_bounds__(FB_WARPS * 32) k_fine_ballot(const uint8_t* __restrict__ act, int n, int nf, int reach,
-                                                                uint32_t* __restrict__ words, int* __restrict__ blockcnt) {
+// cand = 3x3x3 dilation of act: if cand[f >> 1] is clear no coarse voxel within reach of f is active
+// (all candidates lie in [f>>1 - 1, f>>1 + 1] per axis), so most fine voxels cost one byte load.
+__global__ void __launch_bounds__(FB_WARPS * 32) k_fine_ballot(const uint8_t* __restrict__ act, const uint8_t* __restrict__ cand,
+                                                                int n, int nf, int reach, uint32_t* __restrict__ words,
+                                                                int* __restrict__ blockcnt) {
   __shared__ int wc[FB_WARPS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long total = (long long)nf * nf * nf;
@@ -85,8 +90,9 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_fine_ballot(const uint8_t* __
     long long t = base + it * 32 + lane;
     bool on = false;
     if (t < total) {
-      int k = t % nf; long long r = t / nf; int j = r % nf; int i = r / nf;
-      on = fine_active(act, n, reach, i, j, k);
+      const unsigned tu = (unsigned)t;
+      int k = tu % nf; unsigned r = tu / nf; int j = r % nf; int i = r / nf;
+      if (cand[((long long)(i >> 1) * n + (j >> 1)) * n + (k >> 1)]) on = fine_active(act, n, reach, i, j, k);
     }
     uint32_t m = __ballot_sync(0xffffffffu, on);
     if (lane == 0 && base + it * 32 < total) words[(base >> 5) + it] = m;
@@ -181,11 +187,12 @@ int hy3d_refine_level(hy3d_ctx* ctx, const float* d_coarse, int32_t n, float mc_
   if (nfine > 2147483647LL) return hy3d_fail(ctx, HY3D_ERR_UNSUPPORTED, "fine grid too large for int32 indices");
   const long long nwords = (nfine + 31) / 32;
   const int nblocks = (int)ceil_div64(nfine, FB_BLOCK);
-  size_t need = (size_t)nc * 2 + 256;
+  size_t need = (size_t)nc * 3 + 512;
   HY3D_CUDA(ctx, ctx->scratch.reserve(need));
   HY3D_CUDA(ctx, ctx->scratch2.reserve((size_t)nwords * 4 + (size_t)nblocks * 4 + (size_t)(nblocks + 1) * 8 + 1024));
   uint8_t* act = ctx->scratch.as<uint8_t>();
   uint8_t* act2 = act + ((nc + 127) / 128 * 128);
+  uint8_t* cand = act2 + ((nc + 127) / 128 * 128);
   uint32_t* words = ctx->scratch2.as<uint32_t>();
   int* blockcnt = reinterpret_cast<int*>(words + ((nwords + 63) / 64 * 64));
   long long* blockoff = reinterpret_cast<long long*>(blockcnt + ((nblocks + 63) / 64 * 64));
@@ -201,7 +208,10 @@ int hy3d_refine_level(hy3d_ctx* ctx, const float* d_coarse, int32_t n, float mc_
   }
   const int reach = last_level ? 2 : 1;
   HY3D_PROF(ctx, FAM_OCTREE);
-  k_fine_ballot<<<nblocks, FB_WARPS * 32, 0, ctx->stream>>>(mask, n, nf, reach, words, blockcnt);
+  k_dilate3<<<(unsigned)ceil_div64(nc, 256), 256, 0, ctx->stream>>>(mask, n, cand);
+  HY3D_LAUNCH_CHECK(ctx);
+  HY3D_PROF(ctx, FAM_OCTREE);
+  k_fine_ballot<<<nblocks, FB_WARPS * 32, 0, ctx->stream>>>(mask, cand, n, nf, reach, words, blockcnt);
   HY3D_LAUNCH_CHECK(ctx);
   HY3D_PROF(ctx, FAM_OCTREE);
   k_scan_i32<<<1, 1024, 0, ctx->stream>>>(blockcnt, nblocks, blockoff);
