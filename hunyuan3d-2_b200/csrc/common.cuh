@@ -43,6 +43,8 @@ struct DecoderWeights {
   // tcgen05 operand images (decoder_tc.cu)
   DevBuf tc;
   const __half *t_qp, *t_cq, *t_cproj, *t_fc, *t_mp;      // B tiles
+  DevBuf fold;                        // LayerNorm-folded epilogue constants (decoder_tc.cu)
+  const float *cs_q, *bb_q, *cs_fc, *bb_fc, *dotw, *c12;
   const __half* t_cq3;                                    // c_q split [W_hi | W_hi | W_lo], K = 3W (fp32-grade q for KV selection)
 };
 

@@ -50,7 +50,25 @@ struct GemmTC {
   uint8_t* Tout;         // T16 (EPI_Q, EPI_GELU)
   float* Fout;           // row-major fp32 [P, N] (EPI_QF32)
   const float* qn_w; const float* qn_b; int qk_norm; float qscale;   // EPI_Q
+  // LayerNorm folded into this GEMM: the A operand is the RAW row (fp16), W was pre-multiplied by gamma,
+  // so  LN(x) W^T = rstd * (x W'^T - mean * cs) + (beta W^T + bias);  row statistics come as S partial
+  // (mean, M2) slots written by the producer's epilogue and are merged here (Chan et al.), deterministically.
+  const float* st_in; int st_slots; const float* cs; float ln_eps;
+  // statistics of the rows this GEMM produces (EPI_X0 / EPI_RES): slot nb*2+half <- (mean, M2[, dot with dotw])
+  float* st_out; int st_k; const float* dotw;
+  uint8_t* Tcopy;        // fp16 T16 copy of the fp32 rows written to Rout (operand of the next GEMM)
 };
+
+// merge S partial (mean, M2) pairs of n_p samples each -> (mean, rstd)
+__device__ __forceinline__ void merge_row_stats(const float* __restrict__ st, int S, int stride, int n_p, float eps, float& mean,
+                                                float& rstd) {
+  float ms = 0.f;
+  for (int i = 0; i < S; ++i) ms += __ldg(st + i * stride);
+  mean = ms / (float)S;
+  float M2 = 0.f;
+  for (int i = 0; i < S; ++i) { const float d = __ldg(st + i * stride) - mean; M2 += __ldg(st + i * stride + 1) + (float)n_p * d * d; }
+  rstd = rsqrtf(M2 / (float)(S * n_p) + eps);
+}
 
 // exact-erf GELU (reference attention_blocks.py:177) without erff's two divergent branches:
 // 1 - erf(t) = 2^(-t g(t)), g a degree-5 minimax fit on [0,4] (tools fit: |erf err| < 3e-7,
@@ -155,6 +173,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(GemmTC g) {
       fence_after_sync();
       const uint32_t trow = tmem + acc * BN + ((uint32_t)(q * 32) << 16);
       const int col0 = nb * BN + half * (BN / 2);          // first global column of this warp's half
+      float ln_mean = 0.f, ln_rstd = 1.f;
+      if (g.st_in) merge_row_stats(g.st_in + ((size_t)mb * TILE_M + r) * g.st_slots * 2, g.st_slots, 2, g.KB * 64 / g.st_slots,
+                                   g.ln_eps, ln_mean, ln_rstd);
       if constexpr (EPI == EPI_Q || EPI == EPI_QF32) {
 #pragma unroll 1
         for (int hh = 0; hh < 2; ++hh) {                    // two 64-column heads per half
@@ -165,7 +186,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(GemmTC g) {
           const int c = col0 + hh * 64;
           float x[64];
 #pragma unroll
-          for (int i = 0; i < 64; ++i) x[i] = __uint_as_float(v[i]) + (g.bias ? __ldg(g.bias + c + i) : 0.f);
+          {
+            const float4* b4 = reinterpret_cast<const float4*>(g.bias + c);
+            const float4* c4 = reinterpret_cast<const float4*>(g.cs + c);
+            const float nm = -ln_rstd * ln_mean;
+#pragma unroll
+            for (int i4 = 0; i4 < 16; ++i4) {
+              const float4 bv = g.bias ? __ldg(b4 + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
+              float a0 = __uint_as_float(v[4 * i4]), a1 = __uint_as_float(v[4 * i4 + 1]);
+              float a2 = __uint_as_float(v[4 * i4 + 2]), a3 = __uint_as_float(v[4 * i4 + 3]);
+              if (g.st_in) {
+                const float4 cv = __ldg(c4 + i4);
+                a0 = fmaf(ln_rstd, a0, nm * cv.x); a1 = fmaf(ln_rstd, a1, nm * cv.y);
+                a2 = fmaf(ln_rstd, a2, nm * cv.z); a3 = fmaf(ln_rstd, a3, nm * cv.w);
+              }
+              x[4 * i4] = a0 + bv.x; x[4 * i4 + 1] = a1 + bv.y; x[4 * i4 + 2] = a2 + bv.z; x[4 * i4 + 3] = a3 + bv.w;
+            }
+          }
           if (g.qk_norm) {
             float s = 0.f;
 #pragma unroll
@@ -176,7 +213,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(GemmTC g) {
             for (int i = 0; i < 64; ++i) { float d = x[i] - mean; var += d * d; }
             const float rstd = rsqrtf(var * (1.f / 64.f) + 1e-6f);
 #pragma unroll
-            for (int i = 0; i < 64; ++i) x[i] = ((x[i] - mean) * rstd * __ldg(g.qn_w + i) + __ldg(g.qn_b + i)) * g.qscale;
+            for (int i4 = 0; i4 < 16; ++i4) {
+              const float4 gw = __ldg(reinterpret_cast<const float4*>(g.qn_w) + i4), gb = __ldg(reinterpret_cast<const float4*>(g.qn_b) + i4);
+              x[4 * i4] = ((x[4 * i4] - mean) * rstd * gw.x + gb.x) * g.qscale;
+              x[4 * i4 + 1] = ((x[4 * i4 + 1] - mean) * rstd * gw.y + gb.y) * g.qscale;
+              x[4 * i4 + 2] = ((x[4 * i4 + 2] - mean) * rstd * gw.z + gb.z) * g.qscale;
+              x[4 * i4 + 3] = ((x[4 * i4 + 3] - mean) * rstd * gw.w + gb.w) * g.qscale;
+            }
           } else {
 #pragma unroll
             for (int i = 0; i < 64; ++i) x[i] *= g.qscale;
@@ -192,6 +235,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(GemmTC g) {
           }
         }
       } else {
+        float rn = 0.f, rmean = 0.f, rM2 = 0.f, rdot = 0.f;  // running statistics of this thread's 128 output columns
 #pragma unroll 1
         for (int ch = 0; ch < 4; ++ch) {                    // four 32-column chunks per half
           uint32_t v[32];
@@ -199,8 +243,24 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(GemmTC g) {
           tmem_wait_ld();
           const int c = col0 + ch * 32;
           float x[32];
+          {  // per-column constants: warp-uniform 16-byte loads (bias / folded-LN column sums)
+            const float4* b4 = reinterpret_cast<const float4*>(g.bias + c);
+            const float4* c4 = reinterpret_cast<const float4*>(g.cs + c);
+            const bool fold = (EPI == EPI_GELU) && g.st_in != nullptr;
+            const float nm = -ln_rstd * ln_mean;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(v[i]) + (g.bias ? __ldg(g.bias + c + i) : 0.f);
+            for (int i4 = 0; i4 < 8; ++i4) {
+              const float4 bv = g.bias ? __ldg(b4 + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
+              float a0 = __uint_as_float(v[4 * i4]), a1 = __uint_as_float(v[4 * i4 + 1]);
+              float a2 = __uint_as_float(v[4 * i4 + 2]), a3 = __uint_as_float(v[4 * i4 + 3]);
+              if (fold) {      // rstd * (a - mean * cs) + bb
+                const float4 cv = __ldg(c4 + i4);
+                a0 = fmaf(ln_rstd, a0, nm * cv.x); a1 = fmaf(ln_rstd, a1, nm * cv.y);
+                a2 = fmaf(ln_rstd, a2, nm * cv.z); a3 = fmaf(ln_rstd, a3, nm * cv.w);
+              }
+              x[4 * i4] = a0 + bv.x; x[4 * i4 + 1] = a1 + bv.y; x[4 * i4 + 2] = a2 + bv.z; x[4 * i4 + 3] = a3 + bv.w;
+            }
+          }
           if constexpr (EPI == EPI_GELU) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) x[i] = gelu_erf(x[i]);
@@ -218,9 +278,44 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(GemmTC g) {
               if constexpr (EPI == EPI_RES) {
                 const float4 rr = __ldg(reinterpret_cast<const float4*>(g.Rin) + idx);
                 o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+                x[4 * i4] = o.x; x[4 * i4 + 1] = o.y; x[4 * i4 + 2] = o.z; x[4 * i4 + 3] = o.w;
               }
-              reinterpret_cast<float4*>(g.Rout)[idx] = o;
+              if (g.Rout) reinterpret_cast<float4*>(g.Rout)[idx] = o;
             }
+            if (g.Tcopy) {
+              uint8_t* tile = g.Tcopy + ((size_t)mb * (g.N / 64) + (c >> 6)) * TILE_BYTES;
+              const int cbase = (c & 63) >> 3;
+#pragma unroll
+              for (int c16 = 0; c16 < 4; ++c16) store_t16_chunk(tile, r, cbase + c16, x + 8 * c16);
+            }
+            if (g.st_out) {
+              float cs_ = 0.f;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) cs_ += x[i];
+              const float cm = cs_ * (1.f / 32.f);
+              float cM2 = 0.f;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) { const float d = x[i] - cm; cM2 += d * d; }
+              const float delta = cm - rmean, tot = rn + 32.f;
+              rmean += delta * 32.f / tot;
+              rM2 += cM2 + delta * delta * rn * 32.f / tot;
+              rn = tot;
+              if (g.st_k == 3) {
+#pragma unroll
+                for (int i4 = 0; i4 < 8; ++i4) {
+                  const float4 dw = __ldg(reinterpret_cast<const float4*>(g.dotw + c) + i4);
+                  rdot = fmaf(x[4 * i4], dw.x, rdot); rdot = fmaf(x[4 * i4 + 1], dw.y, rdot);
+                  rdot = fmaf(x[4 * i4 + 2], dw.z, rdot); rdot = fmaf(x[4 * i4 + 3], dw.w, rdot);
+                }
+              }
+            }
+          }
+        }
+        if constexpr (EPI == EPI_X0 || EPI == EPI_RES) {
+          if (g.st_out) {
+            float* so = g.st_out + (((size_t)mb * TILE_M + r) * (2 * g.Nb) + nb * 2 + half) * g.st_k;
+            so[0] = rmean; so[1] = rM2;
+            if (g.st_k == 3) so[2] = rdot;
           }
         }
       }
@@ -258,7 +353,7 @@ struct AttnTC {
 // pipe interleaves their MMAs, the SFU-bound softmax phases drift apart instead of marching in step.
 template <bool kHalfExp>
 __global__ void __launch_bounds__(ATT_THREADS, 1) k_attn_tc(AttnTC g) {
-  constexpr float kLazy = kHalfExp ? 1.f : 8.f;
+  constexpr float kLazy = 8.f;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                                   // [2][16 KB]
@@ -409,57 +504,40 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) k_attn_tc(AttnTC g) {
         float m_new = m;
         if (j == 0) { m_new = mx; }
         else if (mx > m + kLazy) { m_new = mx; need = true; }   // lazy rescale: keep the old max while p <= 2^kLazy
-        if (j > 0) {
-          mbar_wait(PVDONE(a), pv_ph); pv_ph ^= 1;            // P buffer free, O holds tiles < j
+        // PV(j-1) must be complete before O is rescaled or the single P buffer is overwritten.  The
+        // rescale is rare (lazy threshold): normally the wait is deferred until this tile's
+        // probabilities sit packed in registers, so the MMA has the whole exp phase to finish.
+        bool waited = (j == 0);
+        if (j > 0 && __any_sync(0xffffffffu, need)) {
+          mbar_wait(PVDONE(a), pv_ph); pv_ph ^= 1; waited = true;
           fence_after_sync();
-          if (__any_sync(0xffffffffu, need)) {
-            const float sc = need ? ex2(m - m_new) : 1.f;
-            l *= sc;
+          const float sc = need ? ex2(m - m_new) : 1.f;
+          l *= sc;
 #pragma unroll 1
-            for (int c = 0; c < 2; ++c) {
-              uint32_t ov[32];
-              HY3D_TMEM_LD32(t_o + c * 32, ov);
-              tmem_wait_ld();
+          for (int c = 0; c < 2; ++c) {
+            uint32_t ov[32];
+            HY3D_TMEM_LD32(t_o + c * 32, ov);
+            tmem_wait_ld();
 #pragma unroll
-              for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * sc);
-              HY3D_TMEM_ST32(t_o + c * 32, ov);
-            }
-            tmem_wait_st();
+            for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * sc);
+            HY3D_TMEM_ST32(t_o + c * 32, ov);
           }
+          tmem_wait_st();
         }
         m = m_new;
-        if constexpr (kHalfExp) {
-          // exp2 on packed halves: one MUFU op yields two probabilities already in the fp16 form the
-          // P tile needs (x = s - m is formed in fp32; |x| <= kLazy near the row maximum keeps the
-          // half rounding of x below the fp16 rounding of p itself).
-          float suma = 0.f, sumb = 0.f;
+        float sum4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int c16 = 0; c16 < 16; ++c16) {
-            uint32_t u[4];
-            __half2 acc = __float2half2_rn(0.f);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const __half2 xh = __floats2half2_rn(__uint_as_float(sv[c16 * 8 + 2 * i]) - m, __uint_as_float(sv[c16 * 8 + 2 * i + 1]) - m);
-              const __half2 ph = ex2_h2(xh);
-              u[i] = *reinterpret_cast<const uint32_t*>(&ph);
-              acc = __hadd2(acc, ph);
-            }
-            const float2 af = __half22float2(acc);
-            suma += af.x; sumb += af.y;
-            *reinterpret_cast<uint4*>(sPa + (c16 >> 3) * TILE_BYTES + sw128_off(r, c16 & 7)) = make_uint4(u[0], u[1], u[2], u[3]);
-          }
-          l += suma + sumb;
-        } else {
-          float sum4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-          for (int c16 = 0; c16 < 16; ++c16) {
-            float p[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { p[i] = ex2(__uint_as_float(sv[c16 * 8 + i]) - m); sum4[i & 3] += p[i]; }
-            store_t16_chunk(sPa + (c16 >> 3) * TILE_BYTES, r, c16 & 7, p);
-          }
-          l += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
+        for (int i = 0; i < 64; ++i) {                       // in place: sv[i] <- packed (p[2i], p[2i+1])
+          const float p0 = ex2(__uint_as_float(sv[2 * i]) - m), p1 = ex2(__uint_as_float(sv[2 * i + 1]) - m);
+          sum4[i & 1] += p0; sum4[2 + (i & 1)] += p1;
+          sv[i] = pack_h2(p0, p1);
         }
+        l += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
+        if (!waited) { mbar_wait(PVDONE(a), pv_ph); pv_ph ^= 1; }
+#pragma unroll
+        for (int c16 = 0; c16 < 16; ++c16)
+          *reinterpret_cast<uint4*>(sPa + (c16 >> 3) * TILE_BYTES + sw128_off(r, c16 & 7)) =
+              make_uint4(sv[4 * c16], sv[4 * c16 + 1], sv[4 * c16 + 2], sv[4 * c16 + 3]);
         fence_proxy_async_smem();
         fence_before_sync();
         __syncwarp();
@@ -618,6 +696,64 @@ __global__ void __launch_bounds__(128) k_head_tc(const float* __restrict__ R, in
   out[oi] = dot + __ldg(bout);
 }
 
+// logits from the per-row partial statistics of x2 written by the last GEMM's epilogue:
+// [ln_post](x2) . wout + bout = rstd * (dot(x2, gamma*wout) - mean * C1) + C2   (C1 = sum gamma*wout, C2 = beta.wout + bout)
+__global__ void __launch_bounds__(128) k_head_final(const float* __restrict__ st, int S, int n_p, int ln_post, const float* __restrict__ c12,
+                                                     QuerySource src, long long n, float* __restrict__ out, int out_mode) {
+  const long long qi = (long long)blockIdx.x * TILE_M + threadIdx.x;
+  if (qi >= n) return;
+  const float* s = st + (size_t)qi * S * 3;
+  float dot = 0.f;
+  for (int i = 0; i < S; ++i) dot += __ldg(s + 3 * i + 2);
+  float v;
+  if (ln_post) {
+    float mean, rstd;
+    merge_row_stats(s, S, 3, n_p, 1e-5f, mean, rstd);
+    v = rstd * (dot - mean * __ldg(c12)) + __ldg(c12 + 1);
+  } else {
+    v = dot + __ldg(c12 + 1);
+  }
+  long long oi = qi;
+  if (out_mode == 1) { oi = src.index[qi]; if (oi < 0) return; }
+  out[oi] = v;
+}
+
+// head constants: dotw = gamma_post * wout (or wout), c12 = {sum dotw, beta_post . wout + bout}
+__global__ void __launch_bounds__(256) k_head_consts(const float* __restrict__ gam, const float* __restrict__ bet,
+                                                      const float* __restrict__ wout, const float* __restrict__ bout, int W,
+                                                      float* __restrict__ dotw, float* __restrict__ c12) {
+  __shared__ float r1[256], r2[256];
+  float a = 0.f, b = 0.f;
+  for (int k = threadIdx.x; k < W; k += 256) {
+    const float d = gam ? gam[k] * wout[k] : wout[k];
+    dotw[k] = d; a += d;
+    if (bet) b = fmaf(bet[k], wout[k], b);
+  }
+  r1[threadIdx.x] = a; r2[threadIdx.x] = b;
+  __syncthreads();
+  for (int o = 128; o; o >>= 1) { if (threadIdx.x < o) { r1[threadIdx.x] += r1[threadIdx.x + o]; r2[threadIdx.x] += r2[threadIdx.x + o]; } __syncthreads(); }
+  if (threadIdx.x == 0) { c12[0] = r1[0]; c12[1] = r2[0] + bout[0]; }
+}
+
+// LayerNorm fold: Wf[j][k] = gamma[k] * W[j][k];  cs[j] = sum_k fp16(Wf[j][k]);  bb[j] = sum_k beta[k] W[j][k] + bias[j]
+// (one warp per output row j)
+__global__ void k_fold_ln(const float* __restrict__ Wsrc, const float* __restrict__ gam, const float* __restrict__ bet,
+                          const float* __restrict__ bias, int N, int K, float* __restrict__ Wf, float* __restrict__ cs,
+                          float* __restrict__ bb) {
+  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (j >= N) return;
+  float a = 0.f, b = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float w = Wsrc[(size_t)j * K + k];
+    const float wf = gam[k] * w;
+    Wf[(size_t)j * K + k] = wf;
+    a += __half2float(__float2half_rn(wf));
+    b = fmaf(bet[k], w, b);
+  }
+  for (int o = 16; o; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+  if (lane == 0) { cs[j] = a; bb[j] = b + (bias ? bias[j] : 0.f); }
+}
+
 // ---- operand image builders ----------------------------------------------------------------
 // fp32 row-major W[N, K] (ld = ldw) -> B16 tiles.  mode 0: plain.  mode 1: query_proj split:
 // K_out = 192 = [W_hi | W_hi | W_lo] over the first E columns (zero padded to 64).  mode 2: the same
@@ -713,10 +849,23 @@ int hy3d_tc_prepare_weights(hy3d_ctx* ctx) {
     HY3D_LAUNCH_CHECK(ctx);
     return 0;
   };
+  // ln_1 folded into c_q, ln_3 into c_fc, ln_post into the head (see GemmTC)
+  HY3D_CUDA(ctx, w.fold.reserve((W + W + R * W + R * W + W + 64) * sizeof(float)));
+  HY3D_CUDA(ctx, ctx->ws[10].reserve(R * W * W * sizeof(float)));
+  float* fb = w.fold.as<float>();
+  float* cs_q = fb; float* bb_q = cs_q + W; float* cs_fc = bb_q + W; float* bb_fc = cs_fc + R * W; float* dotw = bb_fc + R * W; float* c12 = dotw + W;
+  float* Wf = ctx->ws[10].as<float>();
   if (int rc = build(w.qp_w, (int)W, 192, w.E, 1, p_qp)) return rc;
-  if (int rc = build(w.cq_w, (int)W, (int)W, (int)W, 0, p_cq)) return rc;
+  k_fold_ln<<<(unsigned)((W + 7) / 8), 256, 0, ctx->stream>>>(w.cq_w, w.ln1_w, w.ln1_b, w.cq_b, (int)W, (int)W, Wf, cs_q, bb_q);
+  HY3D_LAUNCH_CHECK(ctx);
+  if (int rc = build(Wf, (int)W, (int)W, (int)W, 0, p_cq)) return rc;
   if (int rc = build(w.cproj_w, (int)W, (int)W, (int)W, 0, p_cp)) return rc;
-  if (int rc = build(w.fc_w, (int)(R * W), (int)W, (int)W, 0, p_fc)) return rc;
+  k_fold_ln<<<(unsigned)((R * W + 7) / 8), 256, 0, ctx->stream>>>(w.fc_w, w.ln3_w, w.ln3_b, w.fc_b, (int)(R * W), (int)W, Wf, cs_fc, bb_fc);
+  HY3D_LAUNCH_CHECK(ctx);
+  if (int rc = build(Wf, (int)(R * W), (int)W, (int)W, 0, p_fc)) return rc;
+  k_head_consts<<<1, 256, 0, ctx->stream>>>(w.ln_post ? w.lnp_w : nullptr, w.ln_post ? w.lnp_b : nullptr, w.out_w, w.out_b, (int)W, dotw, c12);
+  HY3D_LAUNCH_CHECK(ctx);
+  w.cs_q = cs_q; w.bb_q = bb_q; w.cs_fc = cs_fc; w.bb_fc = bb_fc; w.dotw = dotw; w.c12 = c12;
   if (int rc = build(w.mp_w, (int)W, (int)(R * W), (int)(R * W), 0, p_mp)) return rc;
   __half* p_cq3 = p_mp + n_mp;
   if (int rc = build(w.cq_w, (int)W, (int)(3 * W), (int)W, 2, p_cq3)) return rc;
@@ -745,22 +894,28 @@ static int decode_tc_impl(hy3d_ctx* ctx, const QuerySource& src_in, long long n,
   if (!w.t_qp)
     return hy3d_fail(ctx, HY3D_ERR_UNSUPPORTED, "tcgen05 path needs head_dim 64 and widths that are multiples of 256");
   const int W = w.W, H = w.H, R = w.R;
+  const int S = 2 * (W / BN);                                   // statistic slots per row (one per 128 output columns)
   const long long CH = 131072;                                 // points per chunk (1024 tiles)
   const long long chmax = n < CH ? (n + 127) / 128 * 128 : CH;
   HY3D_CUDA(ctx, ctx->ws[2].reserve((size_t)chmax * W * 4));          // R32 residual stream
-  HY3D_CUDA(ctx, ctx->ws[3].reserve((size_t)chmax * W * 2));          // T16 a (embed / ln / attn out)
-  HY3D_CUDA(ctx, ctx->ws[4].reserve((size_t)chmax * W * 2));          // T16 q
+  HY3D_CUDA(ctx, ctx->ws[3].reserve((size_t)chmax * W * 2));          // T16 a (embed / raw x0 / attn out)
+  HY3D_CUDA(ctx, ctx->ws[4].reserve((size_t)chmax * W * 2));          // T16 q, then raw x1
   HY3D_CUDA(ctx, ctx->ws[5].reserve((size_t)chmax * W * R * 2));      // T16 h
+  HY3D_CUDA(ctx, ctx->ws[9].reserve((size_t)chmax * S * 7 * 4));      // row statistics: x0 (2), x1 (2), x2 (3) per slot
   float* x = ctx->ws[2].as<float>();
   uint8_t* ta = ctx->ws[3].as<uint8_t>();
   uint8_t* tq = ctx->ws[4].as<uint8_t>();
   uint8_t* th = ctx->ws[5].as<uint8_t>();
+  float* st1 = ctx->ws[9].as<float>();
+  float* st3 = st1 + (size_t)chmax * S * 2;
+  float* stp = st3 + (size_t)chmax * S * 2;
   HY3D_CUDA(ctx, cudaFuncSetAttribute(k_attn_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
   HY3D_CUDA(ctx, cudaFuncSetAttribute(k_attn_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
   const float pi_mul = w.include_pi ? 3.14159265358979323846f : 1.f;
   for (long long p0 = 0; p0 < n; p0 += CH) {
     const long long P = (n - p0 < CH) ? (n - p0) : CH;
     const int Pb = (int)((P + 127) / 128);
+    const long long Pp = (long long)Pb * 128;
     QuerySource src = src_in;
     if (src.mode == 0) src.xyz += 3 * p0;
     else if (src.mode == 1) src.first += p0;
@@ -769,25 +924,22 @@ static int decode_tc_impl(hy3d_ctx* ctx, const QuerySource& src_in, long long n,
     k_embed_tc<<<Pb, 128, 0, ctx->stream>>>(src, P, w.F, pi_mul, ta);
     HY3D_LAUNCH_CHECK(ctx);
     GemmTC g{};
-    g.Mb = Pb;
-    // x0 = query_proj(e)
-    g.A = ta; g.B = reinterpret_cast<const uint8_t*>(w.t_qp); g.KB = 3; g.N = W; g.Nb = W / BN; g.bias = w.qp_b; g.Rout = x;
+    // x0 = query_proj(e): fp32 residual + raw fp16 copy + row statistics for the folded ln_1
+    g.Mb = Pb; g.A = ta; g.B = reinterpret_cast<const uint8_t*>(w.t_qp); g.KB = 3; g.N = W; g.Nb = W / BN; g.bias = w.qp_b;
+    g.Rout = x; g.Tcopy = tq; g.st_out = st1; g.st_k = 2;
     if (int rc = launch_gemm<EPI_X0>(ctx, g, FAM_GEMM_QPROJ)) return rc;
-    const long long Pp = (long long)Pb * 128;
     if (int rc = hy3d_debug_keep(ctx, 0, x, (size_t)Pp * W * 4, 1, Pp, W)) return rc;
-    HY3D_PROF(ctx, FAM_LN);
-    k_ln_tc<false><<<Pb, 128, 0, ctx->stream>>>(x, W, w.ln1_w, w.ln1_b, 1e-6f, ta);
-    HY3D_LAUNCH_CHECK(ctx);
-    if (int rc = hy3d_debug_keep(ctx, 1, ta, (size_t)Pp * W * 2, 2, Pp, W)) return rc;
-    // q = q_norm(c_q(ln_1 x0)) * scale * log2e
+    if (int rc = hy3d_debug_keep(ctx, 1, tq, (size_t)Pp * W * 2, 2, Pp, W)) return rc;
+    // q = q_norm(c_q(ln_1 x0)) * scale * log2e      (ln_1 folded: raw x0 operand, statistics applied in the epilogue)
     g = GemmTC{}; g.Mb = Pb;
-    g.A = ta; g.B = reinterpret_cast<const uint8_t*>(w.t_cq); g.KB = W / 64; g.N = W; g.Nb = W / BN; g.bias = w.cq_b; g.Tout = tq;
+    g.A = tq; g.B = reinterpret_cast<const uint8_t*>(w.t_cq); g.KB = W / 64; g.N = W; g.Nb = W / BN; g.bias = w.bb_q; g.Tout = ta;
+    g.st_in = st1; g.st_slots = S; g.cs = w.cs_q; g.ln_eps = 1e-6f;
     g.qn_w = w.qn_w; g.qn_b = w.qn_b; g.qk_norm = w.qk_norm ? 1 : 0; g.qscale = rsqrtf((float)w.D) * LOG2E;
     if (int rc = launch_gemm<EPI_Q>(ctx, g, FAM_GEMM_CQ)) return rc;
-    if (int rc = hy3d_debug_keep(ctx, 2, tq, (size_t)Pp * W * 2, 2, Pp, W)) return rc;
+    if (int rc = hy3d_debug_keep(ctx, 2, ta, (size_t)Pp * W * 2, 2, Pp, W)) return rc;
     {
       AttnTC a{};
-      a.Q = tq; a.O = ta; a.Pb = Pb; a.H = H;
+      a.Q = ta; a.O = tq; a.Pb = Pb; a.H = H;
       if (d_tile_group) {
         a.K = ctx->kvsel.ktile.as<uint8_t>(); a.V = ctx->kvsel.vtile.as<uint8_t>(); a.nkv = ctx->kvsel.nkv;
         a.tile_group = d_tile_group + p0 / 128; a.group_ntok = ctx->kvsel.ntok.as<int>();
@@ -801,29 +953,30 @@ static int decode_tc_impl(hy3d_ctx* ctx, const QuerySource& src_in, long long n,
       else k_attn_tc<false><<<grid, ATT_THREADS, ATT_SMEM, ctx->stream>>>(a);
       HY3D_LAUNCH_CHECK(ctx);
     }
-    if (int rc = hy3d_debug_keep(ctx, 3, ta, (size_t)Pp * W * 2, 2, Pp, W)) return rc;
-    // x1 = x0 + c_proj(attn)
+    if (int rc = hy3d_debug_keep(ctx, 3, tq, (size_t)Pp * W * 2, 2, Pp, W)) return rc;
+    // x1 = x0 + c_proj(attn): fp32 residual in place + raw fp16 copy + statistics for the folded ln_3
     g = GemmTC{}; g.Mb = Pb;
-    g.A = ta; g.B = reinterpret_cast<const uint8_t*>(w.t_cproj); g.KB = W / 64; g.N = W; g.Nb = W / BN; g.bias = w.cproj_b; g.Rin = x; g.Rout = x;
+    g.A = tq; g.B = reinterpret_cast<const uint8_t*>(w.t_cproj); g.KB = W / 64; g.N = W; g.Nb = W / BN; g.bias = w.cproj_b;
+    g.Rin = x; g.Rout = x; g.Tcopy = ta; g.st_out = st3; g.st_k = 2;
     if (int rc = launch_gemm<EPI_RES>(ctx, g, FAM_GEMM_CPROJ)) return rc;
     if (int rc = hy3d_debug_keep(ctx, 4, x, (size_t)Pp * W * 4, 1, Pp, W)) return rc;
-    HY3D_PROF(ctx, FAM_LN);
-    k_ln_tc<false><<<Pb, 128, 0, ctx->stream>>>(x, W, w.ln3_w, w.ln3_b, 1e-6f, ta);
-    HY3D_LAUNCH_CHECK(ctx);
     if (int rc = hy3d_debug_keep(ctx, 5, ta, (size_t)Pp * W * 2, 2, Pp, W)) return rc;
-    // h = gelu(c_fc(ln_3 x1))
+    // h = gelu(c_fc(ln_3 x1))                      (ln_3 folded)
     g = GemmTC{}; g.Mb = Pb;
-    g.A = ta; g.B = reinterpret_cast<const uint8_t*>(w.t_fc); g.KB = W / 64; g.N = W * R; g.Nb = W * R / BN; g.bias = w.fc_b; g.Tout = th;
+    g.A = ta; g.B = reinterpret_cast<const uint8_t*>(w.t_fc); g.KB = W / 64; g.N = W * R; g.Nb = W * R / BN; g.bias = w.bb_fc; g.Tout = th;
+    g.st_in = st3; g.st_slots = S; g.cs = w.cs_fc; g.ln_eps = 1e-6f;
     if (int rc = launch_gemm<EPI_GELU>(ctx, g, FAM_GEMM_FC)) return rc;
     if (int rc = hy3d_debug_keep(ctx, 6, th, (size_t)Pp * W * R * 2, 2, Pp, W * R)) return rc;
-    // x2 = x1 + c_proj(h)
+    // x2 = x1 + c_proj(h): never stored (unless debugging) — only its row statistics and its dot with
+    // gamma_post * w_out, from which k_head_final forms [ln_post] + output_proj
     g = GemmTC{}; g.Mb = Pb;
-    g.A = th; g.B = reinterpret_cast<const uint8_t*>(w.t_mp); g.KB = W * R / 64; g.N = W; g.Nb = W / BN; g.bias = w.mp_b; g.Rin = x; g.Rout = x;
+    g.A = th; g.B = reinterpret_cast<const uint8_t*>(w.t_mp); g.KB = W * R / 64; g.N = W; g.Nb = W / BN; g.bias = w.mp_b;
+    g.Rin = x; g.Rout = ctx->debug_retain ? x : nullptr; g.st_out = stp; g.st_k = 3; g.dotw = w.dotw;
     if (int rc = launch_gemm<EPI_RES>(ctx, g, FAM_GEMM_MLP)) return rc;
     if (int rc = hy3d_debug_keep(ctx, 7, x, (size_t)Pp * W * 4, 1, Pp, W)) return rc;
     float* outp = d_out + (out_mode == 0 ? p0 : 0);
     HY3D_PROF(ctx, FAM_HEAD);
-    k_head_tc<<<Pb, 128, 0, ctx->stream>>>(x, W, w.ln_post ? w.lnp_w : nullptr, w.lnp_b, w.out_w, w.out_b, src, P, outp, out_mode);
+    k_head_final<<<Pb, 128, 0, ctx->stream>>>(stp, S, 128, w.ln_post ? 1 : 0, w.c12, src, P, outp, out_mode);
     HY3D_LAUNCH_CHECK(ctx);
   }
   return 0;
