@@ -99,7 +99,7 @@ int hy3d_create(int device, void* cuda_stream, hy3d_ctx** out) {
   ctx->device = device;
   ctx->stream = (cudaStream_t)cuda_stream;
   ctx->num_sms = prop.multiProcessorCount;
-  if (const char* e = getenv("HY3D_ATTN_HALF_EXP")) ctx->attn_half_exp = atoi(e);
+  if (const char* e = getenv("HY3D_ATTN_POLY")) ctx->attn_poly = atoi(e);
   if (cudaMallocHost(&ctx->pinned, 4096) != cudaSuccess) { delete ctx; return HY3D_ERR_CUDA; }
   *out = ctx;
   return HY3D_OK;

@@ -103,7 +103,7 @@ struct hy3d_ctx {
   void* pinned = nullptr;             // small pinned host buffer for read-backs
   Prof prof;
   // diagnostics: per-stage activations of the last decoded chunk (hy3d_debug_retain / hy3d_debug_fetch)
-  int attn_half_exp = 0;              // attention probabilities via ex2.f16x2 (HY3D_ATTN_HALF_EXP)
+  int attn_poly = 0;                  // of every 8 attention exponentials, how many run on the FMA pipe (HY3D_ATTN_POLY: 0,2,3,4,6)
   int debug_retain = 0;
   DevBuf dbg[8];
   int dbg_layout[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // 0 row-major fp32, 1 R32, 2 T16

@@ -346,12 +346,26 @@ struct AttnTC {
   const int* tile_group; // per q-tile KV group or null
   const int* group_ntok; // valid tokens per group or null
   int Pb, H, nkv, ntok;  // nkv = tiles per (group, head); ntok = valid tokens when group_ntok == null
+  unsigned stagger_ns;   // start delay of head stream 1
 };
 
 // Two fully independent head streams per CTA (own producer thread, MMA-issuing thread, softmax
 // warpgroup, K/V ring and barriers), so that neither stream's waits block the other: the tensor
 // pipe interleaves their MMAs, the SFU-bound softmax phases drift apart instead of marching in step.
-template <bool kHalfExp>
+// exp2 on the FMA/ALU pipes (Cody-Waite split + degree-3 minimax on [-0.5, 0.5], max rel. error 1.6e-4,
+// below the fp16 rounding of the stored probability): the SFU sustains only ~8 ex2/clk/SM on this part, so a
+// fraction kPoly/8 of the exponentials is taken off it (the FlashAttention-4 recipe).
+__device__ __forceinline__ float exp2_poly(float x) {
+  x = fmaxf(x, -126.f);
+  const float t = x + 12582912.f;                 // round to nearest integer in the low mantissa bits
+  const float f = x - (t - 12582912.f);
+  float p = fmaf(5.360121652e-02f, f, 2.423726171e-01f);
+  p = fmaf(p, f, 6.935024858e-01f);
+  p = fmaf(p, f, 9.999481440e-01f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
+template <int kPoly>
 __global__ void __launch_bounds__(ATT_THREADS, 1) k_attn_tc(AttnTC g) {
   constexpr float kLazy = 8.f;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -472,6 +486,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) k_attn_tc(AttnTC g) {
     const uint32_t t_o = tmem + TM_O0 + a * 64 + ((uint32_t)(q * 32) << 16);
     uint8_t* sPa = sP + a * 2 * TILE_BYTES;
     uint32_t sfull_ph = 0, pv_ph = 0;
+    // Both streams are SFU-bound in their exp phase and idle the SFU otherwise: start stream 1 half a tile
+    // period late so that one stream's exp phase overlaps the other's load / max / wait phases.
+    if (a == 1 && g.stagger_ns) __nanosleep(g.stagger_ns);
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
       const int qt = item / HP, h = (item % HP) * 2 + a;
       const int ntok = g.group_ntok ? g.group_ntok[g.tile_group ? g.tile_group[qt] : 0] : g.ntok;
@@ -528,7 +545,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) k_attn_tc(AttnTC g) {
         float sum4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int i = 0; i < 64; ++i) {                       // in place: sv[i] <- packed (p[2i], p[2i+1])
-          const float p0 = ex2(__uint_as_float(sv[2 * i]) - m), p1 = ex2(__uint_as_float(sv[2 * i + 1]) - m);
+          constexpr unsigned kMask = kPoly == 0 ? 0x00u : kPoly == 2 ? 0x22u : kPoly == 3 ? 0x52u : kPoly == 4 ? 0xAAu : 0xEEu;
+          const float x0 = __uint_as_float(sv[2 * i]) - m, x1 = __uint_as_float(sv[2 * i + 1]) - m;
+          const float p0 = ((kMask >> ((2 * i) & 7)) & 1u) ? exp2_poly(x0) : ex2(x0);
+          const float p1 = ((kMask >> ((2 * i + 1) & 7)) & 1u) ? exp2_poly(x1) : ex2(x1);
           sum4[i & 1] += p0; sum4[2 + (i & 1)] += p1;
           sv[i] = pack_h2(p0, p1);
         }
@@ -909,8 +929,11 @@ static int decode_tc_impl(hy3d_ctx* ctx, const QuerySource& src_in, long long n,
   float* st1 = ctx->ws[9].as<float>();
   float* st3 = st1 + (size_t)chmax * S * 2;
   float* stp = st3 + (size_t)chmax * S * 2;
-  HY3D_CUDA(ctx, cudaFuncSetAttribute(k_attn_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
-  HY3D_CUDA(ctx, cudaFuncSetAttribute(k_attn_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
+  HY3D_CUDA(ctx, cudaFuncSetAttribute(k_attn_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
+  HY3D_CUDA(ctx, cudaFuncSetAttribute(k_attn_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
+  HY3D_CUDA(ctx, cudaFuncSetAttribute(k_attn_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
+  HY3D_CUDA(ctx, cudaFuncSetAttribute(k_attn_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
+  HY3D_CUDA(ctx, cudaFuncSetAttribute(k_attn_tc<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
   const float pi_mul = w.include_pi ? 3.14159265358979323846f : 1.f;
   for (long long p0 = 0; p0 < n; p0 += CH) {
     const long long P = (n - p0 < CH) ? (n - p0) : CH;
@@ -939,7 +962,7 @@ static int decode_tc_impl(hy3d_ctx* ctx, const QuerySource& src_in, long long n,
     if (int rc = hy3d_debug_keep(ctx, 2, ta, (size_t)Pp * W * 2, 2, Pp, W)) return rc;
     {
       AttnTC a{};
-      a.Q = ta; a.O = tq; a.Pb = Pb; a.H = H;
+      a.Q = ta; a.O = tq; a.Pb = Pb; a.H = H; a.stagger_ns = 0;
       if (d_tile_group) {
         a.K = ctx->kvsel.ktile.as<uint8_t>(); a.V = ctx->kvsel.vtile.as<uint8_t>(); a.nkv = ctx->kvsel.nkv;
         a.tile_group = d_tile_group + p0 / 128; a.group_ntok = ctx->kvsel.ntok.as<int>();
@@ -949,8 +972,14 @@ static int decode_tc_impl(hy3d_ctx* ctx, const QuerySource& src_in, long long n,
       int items = Pb * (H / 2);
       int grid = items < ctx->num_sms ? items : ctx->num_sms;
       HY3D_PROF(ctx, FAM_ATTN);
-      if (ctx->attn_half_exp) k_attn_tc<true><<<grid, ATT_THREADS, ATT_SMEM, ctx->stream>>>(a);
-      else k_attn_tc<false><<<grid, ATT_THREADS, ATT_SMEM, ctx->stream>>>(a);
+      switch (ctx->attn_poly) {
+        case 0: k_attn_tc<0><<<grid, ATT_THREADS, ATT_SMEM, ctx->stream>>>(a); break;
+        case 2: k_attn_tc<2><<<grid, ATT_THREADS, ATT_SMEM, ctx->stream>>>(a); break;
+        case 3: k_attn_tc<3><<<grid, ATT_THREADS, ATT_SMEM, ctx->stream>>>(a); break;
+        case 6: k_attn_tc<6><<<grid, ATT_THREADS, ATT_SMEM, ctx->stream>>>(a); break;
+        case 4: k_attn_tc<4><<<grid, ATT_THREADS, ATT_SMEM, ctx->stream>>>(a); break;
+        default: k_attn_tc<0><<<grid, ATT_THREADS, ATT_SMEM, ctx->stream>>>(a); break;
+      }
       HY3D_LAUNCH_CHECK(ctx);
     }
     if (int rc = hy3d_debug_keep(ctx, 3, tq, (size_t)Pp * W * 2, 2, Pp, W)) return rc;
