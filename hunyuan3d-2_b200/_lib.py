@@ -39,6 +39,17 @@ class DecoderDesc(C.Structure):
                  "ln_post_w", "ln_post_b", "out_w", "out_b")]
 
 
+class TransformerLayer(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in
+                ("ln1_w", "ln1_b", "c_qkv_w", "c_qkv_b", "c_proj_w", "c_proj_b", "q_norm_w", "q_norm_b", "k_norm_w", "k_norm_b",
+                 "ln2_w", "ln2_b", "c_fc_w", "c_fc_b", "mlp_proj_w", "mlp_proj_b")]
+
+
+class TransformerDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("width", "heads", "layers", "embed_dim", "qk_norm")] + \
+               [("post_kl_w", C.c_void_p), ("post_kl_b", C.c_void_p), ("layer", C.POINTER(TransformerLayer))]
+
+
 class Coords(C.Structure):
     _fields_ = [("mode", C.c_int32), ("cell", C.c_float * 3), ("bmin", C.c_float * 3),
                 ("axis0", C.c_void_p), ("axis1", C.c_void_p), ("axis2", C.c_void_p)]
@@ -53,6 +64,8 @@ SYMBOLS = {
     "hy3d_set_precision": (C.c_int, [C.c_void_p, C.c_int]),
     "hy3d_launch_count": (C.c_int64, [C.c_void_p]),
     "hy3d_set_decoder_weights": (C.c_int, [C.c_void_p, C.POINTER(DecoderDesc)]),
+    "hy3d_set_transformer_weights": (C.c_int, [C.c_void_p, C.POINTER(TransformerDesc)]),
+    "hy3d_transformer_forward": (C.c_int, [C.c_void_p, c_f32p, C.c_int32, c_f32p]),
     "hy3d_prepare_kv": (C.c_int, [C.c_void_p, c_f32p, C.c_int32]),
     "hy3d_decode_points": (C.c_int, [C.c_void_p, c_f32p, C.c_int64, c_f32p]),
     "hy3d_decode_dense": (C.c_int, [C.c_void_p, c_f32p, c_f32p, c_f32p, C.c_int32, C.c_int32, C.c_int32,
@@ -203,6 +216,48 @@ class GeoContext:
         self._keep = []
         self._weights_key = key
         self._kv_key = None
+
+    def set_transformer(self, sd, cfg, key=None):
+        """sd: full ShapeVAE state dict (post_kl.*, transformer.resblocks.*), cfg: ShapeVAEConfig."""
+        if key is not None and key == getattr(self, "_tf_key", None):
+            return
+        self.sync_stream()
+        keep = []
+
+        def g(name):
+            t = sd.get(name)
+            if t is None:
+                return None
+            t = t.detach().to(device=self.device, dtype=torch.float32).contiguous()
+            keep.append(t)
+            return t.data_ptr()
+        L = cfg.num_decoder_layers
+        layers = (TransformerLayer * L)()
+        names = {"ln1_w": "ln_1.weight", "ln1_b": "ln_1.bias", "c_qkv_w": "attn.c_qkv.weight", "c_qkv_b": "attn.c_qkv.bias",
+                 "c_proj_w": "attn.c_proj.weight", "c_proj_b": "attn.c_proj.bias",
+                 "q_norm_w": "attn.attention.q_norm.weight", "q_norm_b": "attn.attention.q_norm.bias",
+                 "k_norm_w": "attn.attention.k_norm.weight", "k_norm_b": "attn.attention.k_norm.bias",
+                 "ln2_w": "ln_2.weight", "ln2_b": "ln_2.bias", "c_fc_w": "mlp.c_fc.weight", "c_fc_b": "mlp.c_fc.bias",
+                 "mlp_proj_w": "mlp.c_proj.weight", "mlp_proj_b": "mlp.c_proj.bias"}
+        for l in range(L):
+            for field, nm in names.items():
+                setattr(layers[l], field, g(f"transformer.resblocks.{l}.{nm}"))
+        d = TransformerDesc()
+        d.width, d.heads, d.layers, d.embed_dim, d.qk_norm = cfg.width, cfg.heads, L, cfg.embed_dim, int(cfg.qk_norm)
+        d.post_kl_w, d.post_kl_b = g("post_kl.weight"), g("post_kl.bias")
+        d.layer = layers
+        self._check(self.lib.hy3d_set_transformer_weights(self.h, C.byref(d)), "hy3d_set_transformer_weights")
+        torch.cuda.current_stream(self.device).synchronize()
+        self._tf_key = key
+        self._tf_width = cfg.width
+
+    def transformer_forward(self, z: torch.Tensor) -> torch.Tensor:
+        """z: [M, embed_dim] -> latents [M, width] float32 (ShapeVAE.forward for one item)."""
+        self.sync_stream()
+        z = z.detach().to(device=self.device, dtype=torch.float32).contiguous()
+        out = torch.empty((z.shape[0], self._tf_width), dtype=torch.float32, device=self.device)
+        self._check(self.lib.hy3d_transformer_forward(self.h, _ptr(z), z.shape[0], _ptr(out)), "hy3d_transformer_forward")
+        return out
 
     def prepare_kv(self, latents: torch.Tensor):
         """latents: [M, latent_width] on this device (any float dtype)."""

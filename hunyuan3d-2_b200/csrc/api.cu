@@ -113,6 +113,8 @@ void hy3d_destroy(hy3d_ctx* ctx) {
   ctx->kv.k32.release(); ctx->kv.v32.release(); ctx->kv.ktile.release(); ctx->kv.vtile.release();
   ctx->mc.bits.release(); ctx->mc.rowcnt.release(); ctx->mc.rowoff.release(); ctx->mc.stats.release();
   for (auto& b : ctx->ws) b.release();
+  { TransformerState& t = ctx->tf; for (DevBuf* b : {&t.tc, &t.f32, &t.x, &t.ta, &t.tq, &t.to, &t.th, &t.kt, &t.vt, &t.st, &t.tz}) b->release(); }
+  ctx->w.fold.release();
   { KVSelState& k = ctx->kvsel; k.ktile.release(); k.vtile.release(); k.ntok.release(); k.sel.release(); k.qs.release(); k.qbar.release(); k.mask.release(); }
   ctx->scratch.release(); ctx->scratch2.release();
   for (auto& b : ctx->dbg) b.release();

@@ -66,6 +66,19 @@ struct KVSelState {
   DevBuf qs, qbar, mask;              // sampled q fp32 [S, W]; group means [G, W]; merge-mode token bitmasks
 };
 
+// Latent transformer (ShapeVAE.forward, reference model.py:186-189) on the tcgen05 path
+struct TransformerState {
+  bool set = false;
+  int L = 0, W = 0, H = 0, E = 0, R = 4, qk_norm = 0;
+  DevBuf tc;                          // fp16 B16 images, 3-term split: post_kl, per layer c_qkv (LN-folded, rows permuted), c_proj, c_fc (LN-folded), mlp.c_proj
+  DevBuf f32;                         // per layer: cs_qkv, bb_qkv, b_proj, cs_fc, bb_fc, b_proj2, q/k norm; post_kl bias
+  std::vector<const uint8_t*> t_qkv, t_proj, t_fc, t_proj2;
+  std::vector<const float*> cs_qkv, bb_qkv, b_proj, cs_fc, bb_fc, b_proj2, qn_w, qn_b, kn_w, kn_b;
+  const uint8_t* t_postkl = nullptr;
+  const float* b_postkl = nullptr;
+  DevBuf x, ta, tq, to, th, kt, vt, st, tz;   // activations of one forward pass
+};
+
 struct McState {
   bool counted = false;
   const float* grid = nullptr;
@@ -97,6 +110,7 @@ struct hy3d_ctx {
   DecoderWeights w;
   KVState kv;
   KVSelState kvsel;
+  TransformerState tf;
   McState mc;
   DevBuf ws[12];                      // decoder workspaces
   DevBuf scratch, scratch2;           // octree / misc

@@ -38,7 +38,7 @@ constexpr int GEMM_STAGES = 4;
 constexpr int GEMM_THREADS = 384;          // warp0 producer, warp1 mma, warp2 tmem, warp3 idle, warps 4..11 epilogue
 constexpr float LOG2E = 1.4426950408889634f;
 
-enum { EPI_X0 = 0, EPI_Q = 1, EPI_RES = 2, EPI_GELU = 3, EPI_QF32 = 4 };
+enum { EPI_X0 = 0, EPI_Q = 1, EPI_RES = 2, EPI_GELU = 3, EPI_QF32 = 4, EPI_QKV = 5 };
 
 struct GemmTC {
   const uint8_t* A;      // T16 tiles [Mb][KB]
@@ -53,10 +53,13 @@ struct GemmTC {
   // LayerNorm folded into this GEMM: the A operand is the RAW row (fp16), W was pre-multiplied by gamma,
   // so  LN(x) W^T = rstd * (x W'^T - mean * cs) + (beta W^T + bias);  row statistics come as S partial
   // (mean, M2) slots written by the producer's epilogue and are merged here (Chan et al.), deterministically.
-  const float* st_in; int st_slots; const float* cs; float ln_eps;
+  const float* st_in; int st_slots; int st_np; const float* cs; float ln_eps;
   // statistics of the rows this GEMM produces (EPI_X0 / EPI_RES): slot nb*2+half <- (mean, M2[, dot with dotw])
   float* st_out; int st_k; const float* dotw;
   uint8_t* Tcopy;        // fp16 T16 copy of the fp32 rows written to Rout (operand of the next GEMM)
+  int split_out;         // Tcopy / Tout(GELU) written as [hi | lo | hi] (3 * N/64 k-blocks): operand of a 3-term split GEMM
+  // EPI_QKV (latent transformer): output columns are [q (W) | k (W) | v (W)], head-contiguous
+  uint8_t* Kout; uint8_t* Vout; const float* kn_w; const float* kn_b; int nkv; int Wq;
 };
 
 // merge S partial (mean, M2) pairs of n_p samples each -> (mean, rstd)
@@ -87,6 +90,17 @@ __device__ __forceinline__ void store_t16_chunk(uint8_t* tile, int r, int c16, c
   u.x = pack_h2(v[0], v[1]); u.y = pack_h2(v[2], v[3]); u.z = pack_h2(v[4], v[5]); u.w = pack_h2(v[6], v[7]);
   *reinterpret_cast<uint4*>(tile + sw128_off(r, c16)) = u;
 }
+
+// fp16 hi/lo split stores of 8 values: chunk c16 of row r in tiles (hi) t0, (lo) t1, (hi) t2
+__device__ __forceinline__ void store_t16_split(uint8_t* t0, uint8_t* t1, uint8_t* t2, int r, int c16, const float* v) {
+  float hi[8], lo[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { hi[i] = __half2float(__float2half_rn(v[i])); lo[i] = v[i] - hi[i]; }
+  store_t16_chunk(t0, r, c16, hi);
+  store_t16_chunk(t1, r, c16, lo);
+  store_t16_chunk(t2, r, c16, hi);
+}
+
 
 // ------------------------------------------------------------------------------------------
 // Persistent warp-specialised GEMM:  C[P, N] = A[P, K] * W[N, K]^T with a fused epilogue.
@@ -174,9 +188,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(GemmTC g) {
       const uint32_t trow = tmem + acc * BN + ((uint32_t)(q * 32) << 16);
       const int col0 = nb * BN + half * (BN / 2);          // first global column of this warp's half
       float ln_mean = 0.f, ln_rstd = 1.f;
-      if (g.st_in) merge_row_stats(g.st_in + ((size_t)mb * TILE_M + r) * g.st_slots * 2, g.st_slots, 2, g.KB * 64 / g.st_slots,
+      if (g.st_in) merge_row_stats(g.st_in + ((size_t)mb * TILE_M + r) * g.st_slots * 2, g.st_slots, 2, g.st_np,
                                    g.ln_eps, ln_mean, ln_rstd);
-      if constexpr (EPI == EPI_Q || EPI == EPI_QF32) {
+      if constexpr (EPI == EPI_Q || EPI == EPI_QF32 || EPI == EPI_QKV) {
 #pragma unroll 1
         for (int hh = 0; hh < 2; ++hh) {                    // two 64-column heads per half
           uint32_t v[64];
@@ -203,7 +217,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(GemmTC g) {
               x[4 * i4] = a0 + bv.x; x[4 * i4 + 1] = a1 + bv.y; x[4 * i4 + 2] = a2 + bv.z; x[4 * i4 + 3] = a3 + bv.w;
             }
           }
-          if (g.qk_norm) {
+          int part = 0;                                       // 0 q, 1 k, 2 v (EPI_QKV); q otherwise
+          if constexpr (EPI == EPI_QKV) part = c / g.Wq;
+          const float* nw = part == 1 ? g.kn_w : g.qn_w;
+          const float* nb = part == 1 ? g.kn_b : g.qn_b;
+          const float oscale = part == 0 ? g.qscale : 1.f;
+          if (g.qk_norm && part < 2) {
             float s = 0.f;
 #pragma unroll
             for (int i = 0; i < 64; ++i) s += x[i];
@@ -214,20 +233,36 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(GemmTC g) {
             const float rstd = rsqrtf(var * (1.f / 64.f) + 1e-6f);
 #pragma unroll
             for (int i4 = 0; i4 < 16; ++i4) {
-              const float4 gw = __ldg(reinterpret_cast<const float4*>(g.qn_w) + i4), gb = __ldg(reinterpret_cast<const float4*>(g.qn_b) + i4);
-              x[4 * i4] = ((x[4 * i4] - mean) * rstd * gw.x + gb.x) * g.qscale;
-              x[4 * i4 + 1] = ((x[4 * i4 + 1] - mean) * rstd * gw.y + gb.y) * g.qscale;
-              x[4 * i4 + 2] = ((x[4 * i4 + 2] - mean) * rstd * gw.z + gb.z) * g.qscale;
-              x[4 * i4 + 3] = ((x[4 * i4 + 3] - mean) * rstd * gw.w + gb.w) * g.qscale;
+              const float4 gw = __ldg(reinterpret_cast<const float4*>(nw) + i4), gb = __ldg(reinterpret_cast<const float4*>(nb) + i4);
+              x[4 * i4] = ((x[4 * i4] - mean) * rstd * gw.x + gb.x) * oscale;
+              x[4 * i4 + 1] = ((x[4 * i4 + 1] - mean) * rstd * gw.y + gb.y) * oscale;
+              x[4 * i4 + 2] = ((x[4 * i4 + 2] - mean) * rstd * gw.z + gb.z) * oscale;
+              x[4 * i4 + 3] = ((x[4 * i4 + 3] - mean) * rstd * gw.w + gb.w) * oscale;
             }
           } else {
 #pragma unroll
-            for (int i = 0; i < 64; ++i) x[i] *= g.qscale;
+            for (int i = 0; i < 64; ++i) x[i] *= oscale;
           }
           if constexpr (EPI == EPI_QF32) {
             float4* o = reinterpret_cast<float4*>(g.Fout + ((size_t)mb * TILE_M + r) * g.N + c);
 #pragma unroll
             for (int i4 = 0; i4 < 16; ++i4) o[i4] = make_float4(x[4 * i4], x[4 * i4 + 1], x[4 * i4 + 2], x[4 * i4 + 3]);
+          } else if constexpr (EPI == EPI_QKV) {
+            const int h = (c - part * g.Wq) >> 6;
+            if (part == 0) {                                  // q: T16 [Mb][H], k-block == head
+              uint8_t* tile = g.Tout + ((size_t)mb * (g.Wq / 64) + h) * TILE_BYTES;
+#pragma unroll
+              for (int c16 = 0; c16 < 8; ++c16) store_t16_chunk(tile, r, c16, x + 8 * c16);
+            } else if (part == 1) {                           // k: K tiles [H][nkv][128 tok x 64]
+              uint8_t* tile = g.Kout + ((size_t)h * g.nkv + mb) * TILE_BYTES;
+#pragma unroll
+              for (int c16 = 0; c16 < 8; ++c16) store_t16_chunk(tile, r, c16, x + 8 * c16);
+            } else {                                          // v: V^T tiles [H][nkv][2][64 d x 64 tok] — transposed 2-byte stores
+              uint8_t* tile = g.Vout + ((size_t)h * g.nkv + mb) * TILE_BYTES + (r >> 6) * (TILE_BYTES / 2) + (r & 7) * 2;
+              const int c16 = (r & 63) >> 3;
+#pragma unroll
+              for (int d = 0; d < 64; ++d) *reinterpret_cast<__half*>(tile + sw128_off(d, c16)) = __float2half_rn(x[d]);
+            }
           } else {
             uint8_t* tile = g.Tout + ((size_t)mb * (g.N / 64) + (c >> 6)) * TILE_BYTES;
 #pragma unroll
@@ -264,10 +299,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(GemmTC g) {
           if constexpr (EPI == EPI_GELU) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) x[i] = gelu_erf(x[i]);
-            uint8_t* tile = g.Tout + ((size_t)mb * (g.N / 64) + (c >> 6)) * TILE_BYTES;
+            const int KBn = g.N / 64;
+            uint8_t* tile = g.Tout + ((size_t)mb * (g.split_out ? 3 : 1) * KBn + (c >> 6)) * TILE_BYTES;
             const int cbase = (c & 63) >> 3;
+            if (g.split_out) {
 #pragma unroll
-            for (int c16 = 0; c16 < 4; ++c16) store_t16_chunk(tile, r, cbase + c16, x + 8 * c16);
+              for (int c16 = 0; c16 < 4; ++c16)
+                store_t16_split(tile, tile + (size_t)KBn * TILE_BYTES, tile + (size_t)2 * KBn * TILE_BYTES, r, cbase + c16, x + 8 * c16);
+            } else {
+#pragma unroll
+              for (int c16 = 0; c16 < 4; ++c16) store_t16_chunk(tile, r, cbase + c16, x + 8 * c16);
+            }
           } else {
             // R32: [mb][c/4][row][4]
             const size_t base = ((size_t)mb * (g.N / 4) + (c >> 2)) * TILE_M + r;
@@ -283,10 +325,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(GemmTC g) {
               if (g.Rout) reinterpret_cast<float4*>(g.Rout)[idx] = o;
             }
             if (g.Tcopy) {
-              uint8_t* tile = g.Tcopy + ((size_t)mb * (g.N / 64) + (c >> 6)) * TILE_BYTES;
+              const int KBn = g.N / 64;
+              uint8_t* tile = g.Tcopy + ((size_t)mb * (g.split_out ? 3 : 1) * KBn + (c >> 6)) * TILE_BYTES;
               const int cbase = (c & 63) >> 3;
+              if (g.split_out) {
 #pragma unroll
-              for (int c16 = 0; c16 < 4; ++c16) store_t16_chunk(tile, r, cbase + c16, x + 8 * c16);
+                for (int c16 = 0; c16 < 4; ++c16)
+                  store_t16_split(tile, tile + (size_t)KBn * TILE_BYTES, tile + (size_t)2 * KBn * TILE_BYTES, r, cbase + c16, x + 8 * c16);
+              } else {
+#pragma unroll
+                for (int c16 = 0; c16 < 4; ++c16) store_t16_chunk(tile, r, cbase + c16, x + 8 * c16);
+              }
             }
             if (g.st_out) {
               float cs_ = 0.f;
@@ -347,6 +396,7 @@ struct AttnTC {
   const int* group_ntok; // valid tokens per group or null
   int Pb, H, nkv, ntok;  // nkv = tiles per (group, head); ntok = valid tokens when group_ntok == null
   unsigned stagger_ns;   // start delay of head stream 1
+  int split_out;         // O written as [hi | lo | hi] over 3H k-blocks (operand of a 3-term split GEMM)
 };
 
 // Two fully independent head streams per CTA (own producer thread, MMA-issuing thread, softmax
@@ -567,7 +617,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) k_attn_tc(AttnTC g) {
       mbar_wait(PVDONE(a), pv_ph); pv_ph ^= 1;
       fence_after_sync();
       const float inv = 1.f / l;
-      uint8_t* tile = g.O + ((size_t)qt * g.H + h) * TILE_BYTES;
+      uint8_t* tile = g.O + ((size_t)qt * (g.split_out ? 3 : 1) * g.H + h) * TILE_BYTES;
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
         uint32_t ov[32];
@@ -576,8 +626,14 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) k_attn_tc(AttnTC g) {
         float x[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(ov[i]) * inv;
+        if (g.split_out) {
 #pragma unroll
-        for (int c16 = 0; c16 < 4; ++c16) store_t16_chunk(tile, r, c * 4 + c16, x + 8 * c16);
+          for (int c16 = 0; c16 < 4; ++c16)
+            store_t16_split(tile, tile + (size_t)g.H * TILE_BYTES, tile + (size_t)2 * g.H * TILE_BYTES, r, c * 4 + c16, x + 8 * c16);
+        } else {
+#pragma unroll
+          for (int c16 = 0; c16 < 4; ++c16) store_t16_chunk(tile, r, c * 4 + c16, x + 8 * c16);
+        }
       }
       fence_before_sync();
     }
@@ -757,21 +813,25 @@ __global__ void __launch_bounds__(256) k_head_consts(const float* __restrict__ g
 
 // LayerNorm fold: Wf[j][k] = gamma[k] * W[j][k];  cs[j] = sum_k fp16(Wf[j][k]);  bb[j] = sum_k beta[k] W[j][k] + bias[j]
 // (one warp per output row j)
+// permH > 0: source rows are [head][q|k|v][64] (c_qkv, attention_blocks.py:318-321), output rows [q | k | v] head-contiguous.
+// exact_cs: column sums of the unrounded folded weight (3-term split GEMMs) instead of its fp16 rounding.
 __global__ void k_fold_ln(const float* __restrict__ Wsrc, const float* __restrict__ gam, const float* __restrict__ bet,
                           const float* __restrict__ bias, int N, int K, float* __restrict__ Wf, float* __restrict__ cs,
-                          float* __restrict__ bb) {
+                          float* __restrict__ bb, int permH, int exact_cs) {
   const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (j >= N) return;
+  int jd = j;
+  if (permH) { const int h = j / 192, p = (j % 192) / 64, d = j % 64; jd = p * (permH * 64) + h * 64 + d; }
   float a = 0.f, b = 0.f;
   for (int k = lane; k < K; k += 32) {
     const float w = Wsrc[(size_t)j * K + k];
-    const float wf = gam[k] * w;
-    Wf[(size_t)j * K + k] = wf;
-    a += __half2float(__float2half_rn(wf));
-    b = fmaf(bet[k], w, b);
+    const float wf = gam ? gam[k] * w : w;
+    Wf[(size_t)jd * K + k] = wf;
+    a += exact_cs ? wf : __half2float(__float2half_rn(wf));
+    if (bet) b = fmaf(bet[k], w, b);
   }
   for (int o = 16; o; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
-  if (lane == 0) { cs[j] = a; bb[j] = b + (bias ? bias[j] : 0.f); }
+  if (lane == 0) { cs[jd] = a; bb[jd] = b + (bias ? bias[j] : 0.f); }
 }
 
 // ---- operand image builders ----------------------------------------------------------------
@@ -876,11 +936,11 @@ int hy3d_tc_prepare_weights(hy3d_ctx* ctx) {
   float* cs_q = fb; float* bb_q = cs_q + W; float* cs_fc = bb_q + W; float* bb_fc = cs_fc + R * W; float* dotw = bb_fc + R * W; float* c12 = dotw + W;
   float* Wf = ctx->ws[10].as<float>();
   if (int rc = build(w.qp_w, (int)W, 192, w.E, 1, p_qp)) return rc;
-  k_fold_ln<<<(unsigned)((W + 7) / 8), 256, 0, ctx->stream>>>(w.cq_w, w.ln1_w, w.ln1_b, w.cq_b, (int)W, (int)W, Wf, cs_q, bb_q);
+  k_fold_ln<<<(unsigned)((W + 7) / 8), 256, 0, ctx->stream>>>(w.cq_w, w.ln1_w, w.ln1_b, w.cq_b, (int)W, (int)W, Wf, cs_q, bb_q, 0, 0);
   HY3D_LAUNCH_CHECK(ctx);
   if (int rc = build(Wf, (int)W, (int)W, (int)W, 0, p_cq)) return rc;
   if (int rc = build(w.cproj_w, (int)W, (int)W, (int)W, 0, p_cp)) return rc;
-  k_fold_ln<<<(unsigned)((R * W + 7) / 8), 256, 0, ctx->stream>>>(w.fc_w, w.ln3_w, w.ln3_b, w.fc_b, (int)(R * W), (int)W, Wf, cs_fc, bb_fc);
+  k_fold_ln<<<(unsigned)((R * W + 7) / 8), 256, 0, ctx->stream>>>(w.fc_w, w.ln3_w, w.ln3_b, w.fc_b, (int)(R * W), (int)W, Wf, cs_fc, bb_fc, 0, 0);
   HY3D_LAUNCH_CHECK(ctx);
   if (int rc = build(Wf, (int)(R * W), (int)W, (int)W, 0, p_fc)) return rc;
   k_head_consts<<<1, 256, 0, ctx->stream>>>(w.ln_post ? w.lnp_w : nullptr, w.ln_post ? w.lnp_b : nullptr, w.out_w, w.out_b, (int)W, dotw, c12);
@@ -956,7 +1016,7 @@ static int decode_tc_impl(hy3d_ctx* ctx, const QuerySource& src_in, long long n,
     // q = q_norm(c_q(ln_1 x0)) * scale * log2e      (ln_1 folded: raw x0 operand, statistics applied in the epilogue)
     g = GemmTC{}; g.Mb = Pb;
     g.A = tq; g.B = reinterpret_cast<const uint8_t*>(w.t_cq); g.KB = W / 64; g.N = W; g.Nb = W / BN; g.bias = w.bb_q; g.Tout = ta;
-    g.st_in = st1; g.st_slots = S; g.cs = w.cs_q; g.ln_eps = 1e-6f;
+    g.st_in = st1; g.st_slots = S; g.st_np = 128; g.cs = w.cs_q; g.ln_eps = 1e-6f;
     g.qn_w = w.qn_w; g.qn_b = w.qn_b; g.qk_norm = w.qk_norm ? 1 : 0; g.qscale = rsqrtf((float)w.D) * LOG2E;
     if (int rc = launch_gemm<EPI_Q>(ctx, g, FAM_GEMM_CQ)) return rc;
     if (int rc = hy3d_debug_keep(ctx, 2, ta, (size_t)Pp * W * 2, 2, Pp, W)) return rc;
@@ -993,7 +1053,7 @@ static int decode_tc_impl(hy3d_ctx* ctx, const QuerySource& src_in, long long n,
     // h = gelu(c_fc(ln_3 x1))                      (ln_3 folded)
     g = GemmTC{}; g.Mb = Pb;
     g.A = ta; g.B = reinterpret_cast<const uint8_t*>(w.t_fc); g.KB = W / 64; g.N = W * R; g.Nb = W * R / BN; g.bias = w.bb_fc; g.Tout = th;
-    g.st_in = st3; g.st_slots = S; g.cs = w.cs_fc; g.ln_eps = 1e-6f;
+    g.st_in = st3; g.st_slots = S; g.st_np = 128; g.cs = w.cs_fc; g.ln_eps = 1e-6f;
     if (int rc = launch_gemm<EPI_GELU>(ctx, g, FAM_GEMM_FC)) return rc;
     if (int rc = hy3d_debug_keep(ctx, 6, th, (size_t)Pp * W * R * 2, 2, Pp, W * R)) return rc;
     // x2 = x1 + c_proj(h): never stored (unless debugging) — only its row statistics and its dot with
@@ -1055,6 +1115,185 @@ int hy3d_tc_sample_q(hy3d_ctx* ctx, const QuerySource& src_in, long long n, floa
     if (int rc = launch_gemm<EPI_QF32>(ctx, g, FAM_SELECT)) return rc;
   }
   return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Latent transformer: post_kl + L pre-LN self-attention blocks (reference model.py:186-189,
+// attention_blocks.py:301-432) on the same kernels.  Every GEMM is a 3-term split (fp32-grade);
+// the LayerNorms are folded into c_qkv / c_fc; c_qkv's output columns are permuted to [q | k | v].
+// ------------------------------------------------------------------------------------------
+namespace {
+
+// fp32 rows [M, K] -> T16 split [hi | lo | hi]
+__global__ void k_rows_to_t16_split(const float* __restrict__ src, int M, int K, uint8_t* __restrict__ T) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // one 8-element chunk per thread
+  const int c8n = K / 8;
+  const long long rows_p = (long long)((M + 127) / 128) * 128;
+  if (t >= rows_p * c8n) return;
+  const int c8 = (int)(t % c8n); const long long row = t / c8n;
+  const int KBn = K / 64;
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = row < M ? src[row * K + c8 * 8 + i] : 0.f;
+  uint8_t* t0 = T + ((size_t)(row / 128) * 3 * KBn + (c8 >> 3)) * TILE_BYTES;
+  store_t16_split(t0, t0 + (size_t)KBn * TILE_BYTES, t0 + (size_t)2 * KBn * TILE_BYTES, (int)(row % 128), c8 & 7, v);
+}
+
+__global__ void k_r32_to_rows(const float* __restrict__ R, long long rows, int W, float* __restrict__ out) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= rows * (W / 4)) return;
+  const long long row = t / (W / 4); const int c4 = (int)(t % (W / 4));
+  const float4 v = reinterpret_cast<const float4*>(R)[((row / 128) * (W / 4) + c4) * 128 + (row % 128)];
+  reinterpret_cast<float4*>(out)[row * (W / 4) + c4] = v;
+}
+
+}  // namespace
+
+extern "C" int hy3d_set_transformer_weights(hy3d_ctx* ctx, const hy3d_transformer_desc* d) {
+  if (!ctx || !d || !d->layer) return HY3D_ERR_ARG;
+  HY3D_CUDA(ctx, cudaSetDevice(ctx->device));
+  TransformerState& t = ctx->tf;
+  t.set = false;
+  const size_t W = d->width, H = d->heads, L = d->layers, E = d->embed_dim, R = 4;
+  if (W % 256 || H == 0 || W / H != 64 || E % 64 || L == 0)
+    return hy3d_fail(ctx, HY3D_ERR_UNSUPPORTED, "tcgen05 transformer needs head_dim 64, width %% 256 == 0, embed_dim %% 64 == 0");
+  t.L = (int)L; t.W = (int)W; t.H = (int)H; t.E = (int)E; t.qk_norm = d->qk_norm;
+  const size_t n_pk = W * 3 * E, n_qkv = 3 * W * 3 * W, n_proj = W * 3 * W, n_fc = R * W * 3 * W, n_p2 = W * 3 * R * W;
+  HY3D_CUDA(ctx, t.tc.reserve((n_pk + L * (n_qkv + n_proj + n_fc + n_p2)) * 2));
+  const size_t f_layer = 3 * W + 3 * W + W + R * W + R * W + W + 4 * 64;
+  HY3D_CUDA(ctx, t.f32.reserve((W + L * f_layer + 64) * sizeof(float)));
+  HY3D_CUDA(ctx, ctx->ws[10].reserve(R * W * W * sizeof(float)));
+  float* Wf = ctx->ws[10].as<float>();
+  __half* hp = t.tc.as<__half>();
+  float* fp = t.f32.as<float>();
+  auto build = [&](const float* src, size_t N, size_t K3, size_t ldw, __half* dst) -> int {   // mode 2: [hi | hi | lo]
+    long long total = (long long)N * (K3 / 8);
+    k_build_b16<<<(unsigned)ceil_div64(total, 256), 256, 0, ctx->stream>>>(src, (int)N, (int)K3, (int)ldw, 2, 0, reinterpret_cast<uint8_t*>(dst));
+    HY3D_LAUNCH_CHECK(ctx);
+    return 0;
+  };
+  auto copyf = [&](const float* src, size_t n, float* dst) -> int {
+    HY3D_CUDA(ctx, cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+    return 0;
+  };
+  if (!d->post_kl_w || !d->post_kl_b) return hy3d_fail(ctx, HY3D_ERR_ARG, "post_kl missing");
+  if (int rc = build(d->post_kl_w, W, 3 * E, E, hp)) return rc;
+  t.t_postkl = reinterpret_cast<const uint8_t*>(hp); hp += n_pk;
+  if (int rc = copyf(d->post_kl_b, W, fp)) return rc;
+  t.b_postkl = fp; fp += W;
+  t.t_qkv.assign(L, nullptr); t.t_proj.assign(L, nullptr); t.t_fc.assign(L, nullptr); t.t_proj2.assign(L, nullptr);
+  t.cs_qkv.assign(L, nullptr); t.bb_qkv.assign(L, nullptr); t.b_proj.assign(L, nullptr); t.cs_fc.assign(L, nullptr);
+  t.bb_fc.assign(L, nullptr); t.b_proj2.assign(L, nullptr); t.qn_w.assign(L, nullptr); t.qn_b.assign(L, nullptr);
+  t.kn_w.assign(L, nullptr); t.kn_b.assign(L, nullptr);
+  for (size_t l = 0; l < L; ++l) {
+    const hy3d_transformer_layer& y = d->layer[l];
+    if (!y.ln1_w || !y.ln1_b || !y.c_qkv_w || !y.c_proj_w || !y.c_proj_b || !y.ln2_w || !y.ln2_b || !y.c_fc_w || !y.c_fc_b ||
+        !y.mlp_proj_w || !y.mlp_proj_b)
+      return hy3d_fail(ctx, HY3D_ERR_ARG, "transformer layer %d: a required tensor is NULL", (int)l);
+    if (d->qk_norm && !(y.q_norm_w && y.q_norm_b && y.k_norm_w && y.k_norm_b))
+      return hy3d_fail(ctx, HY3D_ERR_ARG, "transformer layer %d: q/k norm missing", (int)l);
+    float* cs_qkv = fp; float* bb_qkv = cs_qkv + 3 * W; float* b_proj = bb_qkv + 3 * W; float* cs_fc = b_proj + W;
+    float* bb_fc = cs_fc + R * W; float* b_p2 = bb_fc + R * W; float* nrm = b_p2 + W;
+    fp += f_layer;
+    // c_qkv: ln_1 folded, rows permuted [head][q|k|v] -> [q | k | v]
+    k_fold_ln<<<(unsigned)((3 * W + 7) / 8), 256, 0, ctx->stream>>>(y.c_qkv_w, y.ln1_w, y.ln1_b, y.c_qkv_b, (int)(3 * W), (int)W, Wf, cs_qkv,
+                                                                    bb_qkv, (int)H, 1);
+    HY3D_LAUNCH_CHECK(ctx);
+    if (int rc = build(Wf, 3 * W, 3 * W, W, hp)) return rc;
+    t.t_qkv[l] = reinterpret_cast<const uint8_t*>(hp); hp += n_qkv;
+    if (int rc = build(y.c_proj_w, W, 3 * W, W, hp)) return rc;
+    t.t_proj[l] = reinterpret_cast<const uint8_t*>(hp); hp += n_proj;
+    k_fold_ln<<<(unsigned)((R * W + 7) / 8), 256, 0, ctx->stream>>>(y.c_fc_w, y.ln2_w, y.ln2_b, y.c_fc_b, (int)(R * W), (int)W, Wf, cs_fc,
+                                                                    bb_fc, 0, 1);
+    HY3D_LAUNCH_CHECK(ctx);
+    if (int rc = build(Wf, R * W, 3 * W, W, hp)) return rc;
+    t.t_fc[l] = reinterpret_cast<const uint8_t*>(hp); hp += n_fc;
+    if (int rc = build(y.mlp_proj_w, W, 3 * R * W, R * W, hp)) return rc;
+    t.t_proj2[l] = reinterpret_cast<const uint8_t*>(hp); hp += n_p2;
+    if (int rc = copyf(y.c_proj_b, W, b_proj)) return rc;
+    if (int rc = copyf(y.mlp_proj_b, W, b_p2)) return rc;
+    if (d->qk_norm) {
+      if (int rc = copyf(y.q_norm_w, 64, nrm)) return rc;
+      if (int rc = copyf(y.q_norm_b, 64, nrm + 64)) return rc;
+      if (int rc = copyf(y.k_norm_w, 64, nrm + 128)) return rc;
+      if (int rc = copyf(y.k_norm_b, 64, nrm + 192)) return rc;
+    }
+    t.cs_qkv[l] = cs_qkv; t.bb_qkv[l] = bb_qkv; t.b_proj[l] = b_proj; t.cs_fc[l] = cs_fc; t.bb_fc[l] = bb_fc; t.b_proj2[l] = b_p2;
+    t.qn_w[l] = nrm; t.qn_b[l] = nrm + 64; t.kn_w[l] = nrm + 128; t.kn_b[l] = nrm + 192;
+  }
+  HY3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // the fold scratch (ws[10]) is reused by other calls
+  t.set = true;
+  return HY3D_OK;
+}
+
+extern "C" int hy3d_transformer_forward(hy3d_ctx* ctx, const float* d_z, int32_t M, float* d_out) {
+  if (!ctx || !d_z || !d_out || M <= 0) return HY3D_ERR_ARG;
+  TransformerState& t = ctx->tf;
+  if (!t.set) return hy3d_fail(ctx, HY3D_ERR_STATE, "transformer weights not set");
+  if (M % 128) return hy3d_fail(ctx, HY3D_ERR_UNSUPPORTED, "token count must be a multiple of 128");
+  HY3D_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int W = t.W, H = t.H, R = t.R, E = t.E, Mb = M / 128, S = 2 * (W / BN);
+  const size_t Mp = (size_t)M;
+  HY3D_CUDA(ctx, t.x.reserve(Mp * W * 4));
+  HY3D_CUDA(ctx, t.ta.reserve(Mp * 3 * W * 2));
+  HY3D_CUDA(ctx, t.tq.reserve(Mp * W * 2));
+  HY3D_CUDA(ctx, t.to.reserve(Mp * 3 * W * 2));
+  HY3D_CUDA(ctx, t.th.reserve(Mp * 3 * R * W * 2));
+  HY3D_CUDA(ctx, t.kt.reserve(Mp * W * 2));
+  HY3D_CUDA(ctx, t.vt.reserve(Mp * W * 2));
+  HY3D_CUDA(ctx, t.st.reserve(Mp * S * 2 * 2 * 4));
+  HY3D_CUDA(ctx, t.tz.reserve(Mp * 3 * E * 2));
+  float* x = t.x.as<float>();
+  uint8_t *ta = t.ta.as<uint8_t>(), *tq = t.tq.as<uint8_t>(), *to = t.to.as<uint8_t>(), *th = t.th.as<uint8_t>();
+  float* stA = t.st.as<float>(); float* stB = stA + Mp * S * 2;
+  HY3D_CUDA(ctx, cudaFuncSetAttribute(k_attn_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
+  {
+    long long total = (long long)M * (E / 8);
+    HY3D_PROF(ctx, FAM_KV);
+    k_rows_to_t16_split<<<(unsigned)ceil_div64(total, 256), 256, 0, ctx->stream>>>(d_z, M, E, t.tz.as<uint8_t>());
+    HY3D_LAUNCH_CHECK(ctx);
+  }
+  GemmTC g{};
+  g.Mb = Mb; g.A = t.tz.as<uint8_t>(); g.B = t.t_postkl; g.KB = 3 * E / 64; g.N = W; g.Nb = W / BN; g.bias = t.b_postkl;
+  g.Rout = x; g.Tcopy = ta; g.split_out = 1; g.st_out = stA; g.st_k = 2;
+  if (int rc = launch_gemm<EPI_X0>(ctx, g, FAM_KV)) return rc;
+  for (int l = 0; l < t.L; ++l) {
+    g = GemmTC{}; g.Mb = Mb;                                   // q, k, v = split(c_qkv(ln_1 x)), q/k norms
+    g.A = ta; g.B = t.t_qkv[l]; g.KB = 3 * W / 64; g.N = 3 * W; g.Nb = 3 * W / BN; g.bias = t.bb_qkv[l];
+    g.st_in = stA; g.st_slots = S; g.st_np = 128; g.cs = t.cs_qkv[l]; g.ln_eps = 1e-6f;
+    g.Tout = tq; g.Kout = t.kt.as<uint8_t>(); g.Vout = t.vt.as<uint8_t>(); g.nkv = Mb; g.Wq = W;
+    g.qn_w = t.qn_w[l]; g.qn_b = t.qn_b[l]; g.kn_w = t.kn_w[l]; g.kn_b = t.kn_b[l]; g.qk_norm = t.qk_norm;
+    g.qscale = rsqrtf(64.f) * LOG2E;
+    if (int rc = launch_gemm<EPI_QKV>(ctx, g, FAM_KV)) return rc;
+    {
+      AttnTC a{};
+      a.Q = tq; a.O = to; a.Pb = Mb; a.H = H; a.K = t.kt.as<uint8_t>(); a.V = t.vt.as<uint8_t>(); a.nkv = Mb; a.ntok = M; a.split_out = 1;
+      int items = Mb * (H / 2);
+      int grid = items < ctx->num_sms ? items : ctx->num_sms;
+      HY3D_PROF(ctx, FAM_KV);
+      k_attn_tc<0><<<grid, ATT_THREADS, ATT_SMEM, ctx->stream>>>(a);
+      HY3D_LAUNCH_CHECK(ctx);
+    }
+    g = GemmTC{}; g.Mb = Mb;                                   // x += c_proj(attn)
+    g.A = to; g.B = t.t_proj[l]; g.KB = 3 * W / 64; g.N = W; g.Nb = W / BN; g.bias = t.b_proj[l];
+    g.Rin = x; g.Rout = x; g.Tcopy = ta; g.split_out = 1; g.st_out = stB; g.st_k = 2;
+    if (int rc = launch_gemm<EPI_RES>(ctx, g, FAM_KV)) return rc;
+    g = GemmTC{}; g.Mb = Mb;                                   // h = gelu(c_fc(ln_2 x))
+    g.A = ta; g.B = t.t_fc[l]; g.KB = 3 * W / 64; g.N = R * W; g.Nb = R * W / BN; g.bias = t.bb_fc[l];
+    g.st_in = stB; g.st_slots = S; g.st_np = 128; g.cs = t.cs_fc[l]; g.ln_eps = 1e-6f; g.Tout = th; g.split_out = 1;
+    if (int rc = launch_gemm<EPI_GELU>(ctx, g, FAM_KV)) return rc;
+    g = GemmTC{}; g.Mb = Mb;                                   // x += c_proj(h)
+    g.A = th; g.B = t.t_proj2[l]; g.KB = 3 * R * W / 64; g.N = W; g.Nb = W / BN; g.bias = t.b_proj2[l];
+    g.Rin = x; g.Rout = x; g.Tcopy = ta; g.split_out = 1; g.st_out = stA; g.st_k = 2;
+    if (int rc = launch_gemm<EPI_RES>(ctx, g, FAM_KV)) return rc;
+  }
+  {
+    long long total = (long long)M * (W / 4);
+    HY3D_PROF(ctx, FAM_KV);
+    k_r32_to_rows<<<(unsigned)ceil_div64(total, 256), 256, 0, ctx->stream>>>(x, M, W, d_out);
+    HY3D_LAUNCH_CHECK(ctx);
+  }
+  return HY3D_OK;
 }
 
 extern "C" int hy3d_debug_watchdog(hy3d_ctx* ctx, int32_t h_out[8]) {

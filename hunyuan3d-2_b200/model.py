@@ -60,10 +60,32 @@ class B200ShapeVAE:
         self.scale_factor = scale_factor
         self.latent_shape = (cfg.num_latents, cfg.embed_dim)
 
-    # -- reference model.py:186-189.  Library GEMM/SDPA (cuBLAS + torch SDPA): this is SURVEY
-    #    §8(f) rank 1 ("next"), not yet a hand-written kernel; ~1.9 TFLOP once per latent.
+    def _tc_ok(self, latents) -> bool:
+        c = self.cfg
+        return (self.device.type == "cuda" and latents.shape[-2] % 128 == 0 and c.width % 256 == 0 and c.width // c.heads == 64
+                and c.embed_dim % 64 == 0 and c.num_decoder_layers > 0)
+
     @torch.no_grad()
-    def forward(self, latents: torch.Tensor, dtype=torch.float32) -> torch.Tensor:
+    def forward(self, latents: torch.Tensor, dtype=torch.float32, impl: str = None) -> torch.Tensor:
+        """ShapeVAE.forward (reference model.py:186-189): post_kl + Transformer.
+
+        impl='tc' (default where the shapes allow): hand-written tcgen05 kernels of libhy3dgeo.so
+        (``hy3d_transformer_forward``: 3-term split fp16 GEMMs = fp32-grade, LayerNorms folded, fp16
+        self-attention), float32 result.  impl='torch': cuBLAS + SDPA library ops in ``dtype``
+        (kept for odd shapes and as a cross-check; 47 ms in fp32 for 3072 tokens vs ~5 ms)."""
+        if impl is None:
+            impl = "tc" if self._tc_ok(latents) else "torch"
+        if impl == "tc":
+            from ._lib import get_context
+            ctx = get_context(self.device)
+            ctx.set_transformer(self.sd, self.cfg, key=id(self.sd))
+            z = latents.to(self.device)
+            return torch.stack([ctx.transformer_forward(z[b]) for b in range(z.shape[0])], 0)
+        return self._forward_torch(latents, dtype)
+
+    # Library GEMM/SDPA statement of the same network (cuBLAS + torch SDPA).
+    @torch.no_grad()
+    def _forward_torch(self, latents: torch.Tensor, dtype=torch.float32) -> torch.Tensor:
         sd, H = self.sd, self.cfg.heads
         x = F.linear(latents.to(self.device, dtype), sd["post_kl.weight"].to(dtype), sd["post_kl.bias"].to(dtype))
         for i in range(self.cfg.num_decoder_layers):

@@ -77,6 +77,27 @@ int hy3d_set_precision(hy3d_ctx* ctx, int precision);
 /* Count of kernels this library has launched on ctx since creation (bench `gpu_launches`). */
 int64_t hy3d_launch_count(const hy3d_ctx* ctx);
 
+/* ---- latent transformer: replaces ShapeVAE.forward = post_kl + Transformer (model.py:186-189,
+ * attention_blocks.py:301-432).  fp32 DEVICE pointers, nn.Linear layout, state_dict names
+ * transformer.resblocks.{l}.* (SURVEY App. A.3).  c_qkv_b may be NULL (qkv_bias False). ---------- */
+typedef struct hy3d_transformer_layer {
+  const float* ln1_w; const float* ln1_b;
+  const float* c_qkv_w; const float* c_qkv_b;          /* [3W, W]; rows viewed [head][q64|k64|v64] (attention_blocks.py:318-321) */
+  const float* c_proj_w; const float* c_proj_b;        /* [W, W] */
+  const float* q_norm_w; const float* q_norm_b; const float* k_norm_w; const float* k_norm_b;   /* [64] or NULL */
+  const float* ln2_w; const float* ln2_b;
+  const float* c_fc_w; const float* c_fc_b;            /* [4W, W] */
+  const float* mlp_proj_w; const float* mlp_proj_b;    /* [W, 4W] */
+} hy3d_transformer_layer;
+typedef struct hy3d_transformer_desc {
+  int32_t width, heads, layers, embed_dim, qk_norm;
+  const float* post_kl_w; const float* post_kl_b;      /* [W, embed_dim], [W] */
+  const hy3d_transformer_layer* layer;                 /* HOST array of `layers` entries */
+} hy3d_transformer_desc;
+int hy3d_set_transformer_weights(hy3d_ctx* ctx, const hy3d_transformer_desc* desc);
+/* d_z: fp32 [M, embed_dim] (already divided by scale_factor, pipelines.py:657); d_out: fp32 [M, W]. M % 128 == 0. */
+int hy3d_transformer_forward(hy3d_ctx* ctx, const float* d_z, int32_t M, float* d_out);
+
 /* ---- decoder: replaces CrossAttentionDecoder.forward (attention_blocks.py:483-493) ---- */
 /* Copies / re-lays-out the weights into the context (fp16 UMMA tiles + fp32 originals). */
 int hy3d_set_decoder_weights(hy3d_ctx* ctx, const hy3d_decoder_desc* desc);
