@@ -74,20 +74,22 @@ def decode_dense_sharded(decode_range: Callable[[int, int, torch.Tensor], None],
     counts = [(b - a) * plane for a, b in (slab_planes(n0, r, world) for r in range(world))]
     if to_all:
         return all_gather_ranges(local, counts, group).view(n0, n1, n2)
+    # one batched group of point-to-point copies (a single NCCL group launch; sizes differ per rank)
+    ops, grid = [], None
     if rank == 0:
         grid = torch.empty(n0 * plane, dtype=torch.float32, device=device)
         grid[: counts[0]] = local
-        reqs, off = [], counts[0]
+        off = counts[0]
         for r in range(1, world):
             if counts[r]:
-                reqs.append(dist.irecv(grid[off: off + counts[r]], src=r, group=group))
+                ops.append(dist.P2POp(dist.irecv, grid[off: off + counts[r]], r, group))
             off += counts[r]
-        for q in reqs:
+    elif local.numel():
+        ops.append(dist.P2POp(dist.isend, local, 0, group))
+    if ops:
+        for q in dist.batch_isend_irecv(ops):
             q.wait()
-        return grid.view(n0, n1, n2)
-    if local.numel():
-        dist.send(local, dst=0, group=group)
-    return None
+    return grid.view(n0, n1, n2) if rank == 0 else None
 
 
 def decode_list_sharded(decode_values: Callable[[torch.Tensor], torch.Tensor], index: torch.Tensor, group=None) -> torch.Tensor:
@@ -166,3 +168,24 @@ class ShardedHierarchicalVolumeDecoding:
             outs.append(grid)
             self.last_stats.append({"levels": levels, "queries": queries})
         return torch.stack(outs, 0).to(latents.dtype)
+
+
+def latents2mesh_data_parallel(vae, latents, group=None, dst: int = 0, **kwargs):
+    """Batched latents, whole meshes per GPU (BASELINE config 4): item b of ``latents`` [B, M, C] is decoded by
+    rank ``b % world`` with ``vae.latents2mesh`` (any volume decoder, FlashVDM included — it is batch-1 per call in
+    the reference too, volume_decoders.py:361); the ``Latent2MeshOutput`` objects are gathered on ``dst`` in batch
+    order (``None`` elsewhere).  No data-path collective: only the final object gather."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    B = latents.shape[0]
+    mine = {}
+    for b in range(rank, B, world):
+        mine[b] = vae.latents2mesh(latents[b:b + 1], **kwargs)[0]
+    gathered = [None] * world if rank == dst else None
+    dist.gather_object(mine, gathered, dst=dst, group=group)
+    if rank != dst:
+        return None
+    out = [None] * B
+    for part in gathered:
+        for b, o in part.items():
+            out[b] = o
+    return out

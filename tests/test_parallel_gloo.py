@@ -48,6 +48,11 @@ def _worker(rank, world, port, q):
         vals = P.decode_list_sharded(values, idx, None)
         ijk = np.stack(np.unravel_index(idx.numpy(), (n, n, n)), 1)
         ok = ok and np.array_equal(vals.numpy(), field(torch.from_numpy(OV.refined_coords(ijk, 1.01, 2 * res))).numpy())
+        class FakeVAE:                                   # whole meshes per rank (config 4)
+            def latents2mesh(self, lat, **kw):
+                return [("mesh", int(lat[0, 0, 0]), kw["octree_resolution"])]
+        outs = P.latents2mesh_data_parallel(FakeVAE(), torch.arange(5.).view(5, 1, 1), None, 0, octree_resolution=9)
+        ok = ok and (outs == [("mesh", b, 9) for b in range(5)] if rank == 0 else outs is None)
         lat = P.broadcast_latents(torch.arange(6.).view(2, 3) if rank == 0 else None, (2, 3), "cpu")
         ok = ok and bool((lat == torch.arange(6.).view(2, 3)).all())
         q.put((rank, bool(ok)))
