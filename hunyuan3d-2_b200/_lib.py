@@ -7,6 +7,7 @@ attempt to compute raises ``RuntimeError`` (build it with
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 import os
 import threading
 from typing import Optional
@@ -93,6 +94,8 @@ SYMBOLS = {
     "hy3d_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "hy3d_debug_watchdog": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
     "hy3d_debug_retain": (C.c_int, [C.c_void_p, C.c_int]),
+    "hy3d_debug_experiment": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "hy3d_debug_timers": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "hy3d_debug_fetch": (C.c_int, [C.c_void_p, C.c_int, c_f32p, C.c_int64, C.POINTER(C.c_int32)]),
     "hy3d_mc_cases": (C.c_int, [C.c_void_p, c_f32p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p]),
 }
@@ -172,9 +175,17 @@ class GeoContext:
     def launches(self) -> int:
         return int(self.lib.hy3d_launch_count(self.h))
 
-    def set_decoder(self, sd, cfg, key=None):
-        """sd: decoder state dict (keys without ``geo_decoder.``), cfg: ShapeVAEConfig."""
-        if key is not None and key == self._weights_key:
+    @staticmethod
+    def _same_owner(ref, owner) -> bool:
+        """The cached weights belong to `owner` iff the weak reference taken when they were loaded is still alive
+        and points at it.  id() / data_ptr() values alone are not identities: CPython and the caching allocator
+        hand the same values to new objects once the old ones are freed."""
+        return owner is not None and ref is not None and ref() is owner
+
+    def set_decoder(self, sd, cfg, key=None, owner=None):
+        """sd: decoder state dict (keys without ``geo_decoder.``), cfg: ShapeVAEConfig.  `key` (+ the live `owner`
+        object it was computed from) lets repeated calls with unchanged weights skip the upload."""
+        if key is not None and key == self._weights_key and self._same_owner(getattr(self, "_weights_owner", None), owner):
             return
         self.sync_stream()
         dev = self.device
@@ -215,11 +226,12 @@ class GeoContext:
         torch.cuda.current_stream(self.device).synchronize()     # device->device copies done; staging may go
         self._keep = []
         self._weights_key = key
+        self._weights_owner = weakref.ref(owner) if owner is not None else None
         self._kv_key = None
 
-    def set_transformer(self, sd, cfg, key=None):
+    def set_transformer(self, sd, cfg, key=None, owner=None):
         """sd: full ShapeVAE state dict (post_kl.*, transformer.resblocks.*), cfg: ShapeVAEConfig."""
-        if key is not None and key == getattr(self, "_tf_key", None):
+        if key is not None and key == getattr(self, "_tf_key", None) and self._same_owner(getattr(self, "_tf_owner", None), owner):
             return
         self.sync_stream()
         keep = []
@@ -249,6 +261,7 @@ class GeoContext:
         self._check(self.lib.hy3d_set_transformer_weights(self.h, C.byref(d)), "hy3d_set_transformer_weights")
         torch.cuda.current_stream(self.device).synchronize()
         self._tf_key = key
+        self._tf_owner = weakref.ref(owner) if owner is not None else None
         self._tf_width = cfg.width
 
     def transformer_forward(self, z: torch.Tensor) -> torch.Tensor:
@@ -306,6 +319,14 @@ class GeoContext:
         cnt = (C.c_int64 * 16)()
         self._check(self.lib.hy3d_profile_read(self.h, ms, cnt), "hy3d_profile_read")
         return {f: (ms[i], cnt[i]) for i, f in enumerate(self.FAMILIES)}
+
+    def debug_experiment(self, bits: int = 0, attn_poly: int = 0):
+        self._check(self.lib.hy3d_debug_experiment(self.h, int(bits), int(attn_poly)), "hy3d_debug_experiment")
+
+    def debug_timers(self):
+        out = (C.c_uint64 * 32)()
+        self._check(self.lib.hy3d_debug_timers(self.h, out), "hy3d_debug_timers")
+        return list(out)
 
     def debug_retain(self, enable: bool):
         self._check(self.lib.hy3d_debug_retain(self.h, int(enable)), "hy3d_debug_retain")

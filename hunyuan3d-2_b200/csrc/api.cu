@@ -69,6 +69,13 @@ int hy3d_debug_retain(hy3d_ctx* ctx, int enable) {
   return HY3D_OK;
 }
 
+int hy3d_debug_experiment(hy3d_ctx* ctx, int bits, int attn_poly) {
+  if (!ctx) return HY3D_ERR_ARG;
+  ctx->xbits = bits;
+  ctx->attn_poly = attn_poly;
+  return HY3D_OK;
+}
+
 int hy3d_debug_fetch(hy3d_ctx* ctx, int stage, float* d_out, int64_t rows, int32_t* h_width) {
   if (!ctx || stage < 0 || stage >= 8 || !d_out || !h_width) return HY3D_ERR_ARG;
   if (!ctx->dbg[stage].p) return hy3d_fail(ctx, HY3D_ERR_STATE, "stage %d was not retained", stage);
@@ -100,6 +107,7 @@ int hy3d_create(int device, void* cuda_stream, hy3d_ctx** out) {
   ctx->stream = (cudaStream_t)cuda_stream;
   ctx->num_sms = prop.multiProcessorCount;
   if (const char* e = getenv("HY3D_ATTN_POLY")) ctx->attn_poly = atoi(e);
+  if (const char* e = getenv("HY3D_DBG")) ctx->xbits = atoi(e);
   if (cudaMallocHost(&ctx->pinned, 4096) != cudaSuccess) { delete ctx; return HY3D_ERR_CUDA; }
   *out = ctx;
   return HY3D_OK;
@@ -204,6 +212,10 @@ int hy3d_prepare_kv(hy3d_ctx* ctx, const float* d_latents, int32_t M) {
   if (!ctx || !d_latents || M <= 0) return HY3D_ERR_ARG;
   if (!ctx->w.set) return hy3d_fail(ctx, HY3D_ERR_STATE, "decoder weights not set");
   HY3D_CUDA(ctx, cudaSetDevice(ctx->device));
+  // tensor path: K/V projected by the split-precision tcgen05 GEMMs; HY3D_PRECISION_FP32_SIMT (the on-device
+  // fp32 statement used as a cross-check) and shapes the tensor path does not tile keep the CUDA-core projection
+  if (ctx->precision != HY3D_PRECISION_FP32_SIMT && ctx->w.t_qp && ctx->w.t_ckv3 && !(ctx->xbits & 0x10000))
+    return hy3d_tc_project_kv(ctx, d_latents, M);
   if (int rc = hy3d_simt_prepare_kv(ctx, d_latents, M)) return rc;
   return hy3d_tc_prepare_kv(ctx);
 }

@@ -1,0 +1,427 @@
+// Attention of the tcgen05 decoder chain and of the latent transformer (reference
+// attention_processors.py:29-32 SDPA; attention_blocks.py:184-215 / :301-345): softmax(q k^T) v per head,
+// head dim 64, 128-query tiles, fp16 operands, fp32 accumulation in tensor memory.
+// Included by decoder_tc.cu inside its anonymous namespace (uses TILE_BYTES, store_t16_* and tc::).
+//
+// One CTA iteration = one 128-query tile x 2 heads; each head is an independent *stream* with its own
+//   producer warp  (warp 2a):   Q tile, then K(0), K(1), V(0), K(2), V(1), ... through a ring of 16 KB slots
+//                               (1-D bulk copies: every tile is one contiguous SW128 K-major image)
+//   MMA warp       (warp 2a+1): S = Q K(j)^T  (4 x tcgen05.mma 128x128x16, A and B from shared memory)
+//                               O += P(j) V(j) (8 x tcgen05.mma 128x64x16, A = P from TENSOR memory, B = V^T)
+//   softmax warps:              S -> registers, exponentials, P -> tensor memory as packed fp16 pairs
+// so that neither stream's waits block the other and the tensor pipe interleaves their MMAs.
+// Both single-thread roles run with the whole warp converged and issue through one elected lane (tc::elect_one):
+// under a divergent `if (lane == 0)` ptxas wraps every tcgen05.mma in a ~100-cycle uniform-register waterfall,
+// which alone capped this kernel at ~30 % of the tensor peak.
+// TMEM columns: S[a] (fp32, 128) at a*128; P[a] (fp16 pairs, 64) at 256 + a*64; O[a] (fp32, 64) at 384 + a*64.
+// P never crosses shared memory, whose bandwidth (operand reads + TMA fills) is the scarce resource here.
+//
+// Two softmax bodies:
+//  * k_attn_fast — used when the scores are provably bounded: with q_norm / k_norm (LayerNorm over the 64 head
+//    dims, reference attention_blocks.py:197-198,210-211) |q.k| * scale * log2e <= B, a constant of the norm
+//    weights (attn_score_bound).  For B <= 15.9 no exp2(s) can overflow fp16, so the softmax needs NO running
+//    maximum, no subtraction and no rescaling of O: p = exp2(s) directly — mathematically the same softmax (the
+//    common factor cancels in O / l).  Probabilities below 2^-14 are fp16 subnormals (absolute error <= 2^-25,
+//    i.e. <= 2^-9 of the row's largest term even in the worst case of a row whose every score sits at -B; rows
+//    whose best score is >= -5 — every row of a trained or random model — lose < 2^-20 per term).  Two threads per
+//    query row (16 softmax warps) halve the serial latency of each stream; per element the instruction stream is
+//    MUFU.EX2 + FADD + half a F2FP.
+//  * k_attn_tc — online softmax with a running maximum (lazy rescale) for everything else (no q/k norm, large
+//    norm gains).  One thread per row.
+#pragma once
+
+constexpr int ATT_SLOTS = 5;               // K / V^T ring per stream, 16 KB each
+constexpr int TM_S0 = 0, TM_P0 = 256, TM_O0 = 384;
+constexpr int ATT_THREADS = 384;           // k_attn_tc: 4 role warps + 2 x 4 softmax warps
+constexpr int ATT_FAST_THREADS = 640;      // k_attn_fast: 4 role warps + 2 x 8 softmax warps
+constexpr float ATT_FAST_BOUND = 15.9f;    // exp2(15.9) = 61147 < 65504: no fp16 overflow, ever
+
+struct AttnTC {
+  const uint8_t* Q;      // T16 [Pb][H]  (q already scaled by 1/sqrt(d) * log2e)
+  const uint8_t* K;      // [group][H][nkv][16 KB]
+  const uint8_t* V;      // [group][H][nkv][16 KB]  (V^T: 2 x [64 d x 64 tok] per tile)
+  uint8_t* O;            // T16 [Pb][H]
+  const int* tile_group; // per q-tile KV group or null
+  const int* group_ntok; // valid tokens per group or null
+  int Pb, H, nkv, ntok;  // nkv = tiles per (group, head); ntok = valid tokens when group_ntok == null
+  int split_out;         // O written as [hi | lo | hi] over 3H k-blocks (operand of a 3-term split GEMM)
+  unsigned long long* timers;   // k_attn_fast<.., true>: phase clocks of CTA 0 (see hy3d_debug_timers)
+};
+
+struct AttnBars {                          // mbarrier addresses (shared window), per stream a
+  uint32_t b0;
+  static constexpr int NB = 2 * ATT_SLOTS + 6;
+  __device__ __forceinline__ uint32_t kvfull(int a, int s) const { return b0 + 8u * (a * NB + s); }
+  __device__ __forceinline__ uint32_t kvempty(int a, int s) const { return b0 + 8u * (a * NB + ATT_SLOTS + s); }
+  __device__ __forceinline__ uint32_t qfull(int a) const { return b0 + 8u * (a * NB + 2 * ATT_SLOTS); }
+  __device__ __forceinline__ uint32_t qempty(int a) const { return b0 + 8u * (a * NB + 2 * ATT_SLOTS + 1); }
+  __device__ __forceinline__ uint32_t sfull(int a) const { return b0 + 8u * (a * NB + 2 * ATT_SLOTS + 2); }
+  __device__ __forceinline__ uint32_t sempty(int a) const { return b0 + 8u * (a * NB + 2 * ATT_SLOTS + 3); }
+  __device__ __forceinline__ uint32_t pfull(int a) const { return b0 + 8u * (a * NB + 2 * ATT_SLOTS + 4); }
+  __device__ __forceinline__ uint32_t pvdone(int a) const { return b0 + 8u * (a * NB + 2 * ATT_SLOTS + 5); }
+};
+
+constexpr int ATT_TILES_BYTES = (2 + 2 * ATT_SLOTS) * TILE_BYTES;      // Q[2] + K/V ring[2][SLOTS]
+constexpr size_t ATT_SMEM = 1024 + ATT_TILES_BYTES + 512 + 2048;       // + barriers / TMEM slot + row-sum exchange (fast kernel)
+
+// Shared prologue: barriers, TMEM.  `softmax_warps` = arrivals expected on SEMPTY / PFULL per stream.
+__device__ __forceinline__ uint32_t attn_setup(uint8_t* smem, AttnBars& B, int softmax_warps) {
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATT_TILES_BYTES);
+  B.b0 = smem_u32(bars);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * AttnBars::NB);
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    for (int a = 0; a < 2; ++a) {
+      for (int s = 0; s < ATT_SLOTS; ++s) { mbar_init(B.kvfull(a, s), 1); mbar_init(B.kvempty(a, s), 1); }
+      mbar_init(B.qfull(a), 1); mbar_init(B.qempty(a), 1);
+      mbar_init(B.sfull(a), 1); mbar_init(B.sempty(a), softmax_warps); mbar_init(B.pfull(a), softmax_warps); mbar_init(B.pvdone(a), 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) { tmem_alloc(smem_u32(tmem_slot), 512); tmem_relinquish(); }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  return *tmem_slot;
+}
+
+// Producer warp of stream a (whole warp converged).
+__device__ __forceinline__ void attn_producer(const AttnTC& g, const AttnBars& B, uint8_t* smem, int a) {
+  uint8_t* sQ = smem + a * TILE_BYTES;
+  uint8_t* ring = smem + 2 * TILE_BYTES + a * ATT_SLOTS * TILE_BYTES;
+  const int HP = g.H / 2, nitems = g.Pb * HP, nkv = g.nkv;
+  int s = 0; uint32_t ph = 0, qph = 0;
+  auto push = [&](const uint8_t* src) {
+    mbar_wait(B.kvempty(a, s), ph ^ 1);
+    if (elect_one()) {
+      mbar_arrive_expect_tx(B.kvfull(a, s), TILE_BYTES);
+      bulk_g2s(smem_u32(ring + s * TILE_BYTES), src, TILE_BYTES, B.kvfull(a, s));
+    }
+    __syncwarp();
+    if (++s == ATT_SLOTS) { s = 0; ph ^= 1; }
+  };
+  for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const int qt = item / HP, h = (item % HP) * 2 + a;
+    const int grp = g.tile_group ? g.tile_group[qt] : 0;
+    mbar_wait(B.qempty(a), qph ^ 1);
+    if (elect_one()) {
+      mbar_arrive_expect_tx(B.qfull(a), TILE_BYTES);
+      bulk_g2s(smem_u32(sQ), g.Q + ((size_t)qt * g.H + h) * TILE_BYTES, TILE_BYTES, B.qfull(a));
+    }
+    __syncwarp();
+    qph ^= 1;
+    const uint8_t* kb = g.K + ((size_t)grp * g.H + h) * nkv * TILE_BYTES;
+    const uint8_t* vb = g.V + ((size_t)grp * g.H + h) * nkv * TILE_BYTES;
+    push(kb);
+    for (int j = 0; j < nkv; ++j) {
+      if (j + 1 < nkv) push(kb + (size_t)(j + 1) * TILE_BYTES);
+      push(vb + (size_t)j * TILE_BYTES);
+    }
+  }
+}
+
+// MMA-issuing warp of stream a (whole warp converged, one elected lane issues).
+__device__ __forceinline__ void attn_mma(const AttnTC& g, const AttnBars& B, uint8_t* smem, uint32_t tmem, int a) {
+  uint8_t* sQ = smem + a * TILE_BYTES;
+  uint8_t* ring = smem + 2 * TILE_BYTES + a * ATT_SLOTS * TILE_BYTES;
+  const int HP = g.H / 2, nitems = g.Pb * HP, nkv = g.nkv;
+  const uint32_t idesc_s = make_idesc_f16(128, 128);
+  const uint32_t idesc_o = make_idesc_f16(128, 64);
+  const uint32_t d_s = tmem + TM_S0 + a * 128, d_o = tmem + TM_O0 + a * 64, a_p = tmem + TM_P0 + a * 64;
+  const uint64_t qd = make_desc_sw128(smem_u32(sQ));
+  int s = 0; uint32_t ph = 0, qph = 0, sph = 0, pph = 0;
+  auto issue_s = [&]() {
+    mbar_wait(B.kvfull(a, s), ph);
+    mbar_wait(B.sempty(a), sph ^ 1); sph ^= 1;
+    fence_after_sync();
+    const uint64_t bd = make_desc_sw128(smem_u32(ring + s * TILE_BYTES));
+    if (elect_one()) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) mma_f16_ss(d_s, qd + 2 * k, bd + 2 * k, idesc_s, k != 0);
+      mma_commit(B.kvempty(a, s));
+      mma_commit(B.sfull(a));
+    }
+    __syncwarp();
+    if (++s == ATT_SLOTS) { s = 0; ph ^= 1; }
+  };
+  auto issue_pv = [&](int j) {
+    mbar_wait(B.kvfull(a, s), ph);
+    mbar_wait(B.pfull(a), pph); pph ^= 1;
+    fence_after_sync();
+    const uint64_t bd = make_desc_sw128(smem_u32(ring + s * TILE_BYTES));
+    if (elect_one()) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k)                      // 16 tokens (8 TMEM columns of fp16 pairs) per MMA
+        mma_f16_ts(d_o, a_p + 8 * k, bd + (k >> 2) * (TILE_BYTES / 2 / 16) + 2 * (k & 3), idesc_o, (j | k) != 0);
+      mma_commit(B.kvempty(a, s));
+      mma_commit(B.pvdone(a));
+    }
+    __syncwarp();
+    if (++s == ATT_SLOTS) { s = 0; ph ^= 1; }
+  };
+  for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+    mbar_wait(B.qfull(a), qph); qph ^= 1;
+    fence_after_sync();
+    issue_s();
+    for (int j = 0; j < nkv; ++j) {
+      if (j + 1 < nkv) issue_s();
+      else { if (elect_one()) mma_commit(B.qempty(a)); __syncwarp(); }   // all S MMAs of this item issued: Q may be refilled once they finish
+      issue_pv(j);
+    }
+  }
+}
+
+// exp2 on the FMA/ALU pipes (Cody-Waite split + degree-3 minimax on [-0.5, 0.5], max rel. error 1.6e-4, below the
+// fp16 rounding of the stored probability): takes kPoly of every 8 exponentials off the SFU.
+__device__ __forceinline__ float exp2_poly(float x) {
+  x = fmaxf(x, -126.f);
+  const float t = x + 12582912.f;                 // round to nearest integer in the low mantissa bits
+  const float f = x - (t - 12582912.f);
+  float p = fmaf(5.360121652e-02f, f, 2.423726171e-01f);
+  p = fmaf(p, f, 6.935024858e-01f);
+  p = fmaf(p, f, 9.999481440e-01f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+template <int kPoly>
+__device__ __forceinline__ bool exp_on_fma(int i) {
+  constexpr unsigned kMask = kPoly == 0 ? 0x00u : kPoly == 1 ? 0x10u : kPoly == 2 ? 0x22u : kPoly == 3 ? 0x52u : kPoly == 4 ? 0xAAu : 0xEEu;
+  return ((kMask >> (i & 7)) & 1u) != 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Bounded scores: no running maximum, two threads per query row.
+// ------------------------------------------------------------------------------------------
+template <int kPoly, bool kTimers>
+__global__ void __launch_bounds__(ATT_FAST_THREADS, 1) k_attn_fast(AttnTC g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  AttnBars B;
+  const uint32_t tmem = attn_setup(smem, B, 8);
+  float* lsum = reinterpret_cast<float*>(smem + ATT_TILES_BYTES + 512);   // [2 streams][2 halves][128 rows]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int HP = g.H / 2, nitems = g.Pb * HP, nkv = g.nkv;
+
+  // (no setmaxnreg here: registers can only be moved inside the CTA's launch allocation, 640 x 96, and the
+  //  softmax threads fit in 96)
+  if (warp < 4) {
+    if ((warp & 1) == 0) attn_producer(g, B, smem, warp >> 1);
+    else attn_mma(g, B, smem, tmem, warp >> 1);
+  } else {
+    const int a = (warp - 4) >> 3;                      // head stream
+    const int hh = ((warp - 4) >> 2) & 1;               // column half: tokens [64 hh, 64 hh + 64) of every KV tile
+    const int q = warp & 3;                             // TMEM lane quadrant
+    const int r = q * 32 + lane;                        // query row
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const uint32_t t_s = tmem + TM_S0 + a * 128 + hh * 64 + lane_off;
+    const uint32_t t_p = tmem + TM_P0 + a * 64 + hh * 32 + lane_off;
+    const uint32_t t_o = tmem + TM_O0 + a * 64 + hh * 32 + lane_off;
+    uint32_t sfull_ph = 0, pv_ph = 0;
+    long long tk0 = 0, tk[6] = {0, 0, 0, 0, 0, 0};
+#define HY3D_TICK(i) if constexpr (kTimers) { const long long t_ = clock64(); tk[i] += t_ - tk0; tk0 = t_; }
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+      const int qt = item / HP, h = (item % HP) * 2 + a;
+      const int ntok = g.group_ntok ? g.group_ntok[g.tile_group ? g.tile_group[qt] : 0] : g.ntok;
+      float l0 = 0.f, l1 = 0.f;
+      if constexpr (kTimers) tk0 = clock64();
+      for (int j = 0; j < nkv; ++j) {
+        mbar_wait(B.sfull(a), sfull_ph); sfull_ph ^= 1;
+        fence_after_sync();
+        HY3D_TICK(0)
+        uint32_t sv[64];
+        HY3D_TMEM_LD32(t_s, sv); HY3D_TMEM_LD32(t_s + 32, (sv + 32));
+        tmem_wait_ld();
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(B.sempty(a));       // S is in registers: the next S MMA may overwrite it
+        HY3D_TICK(1)
+        const int valid = ntok - j * 128 - hh * 64;    // columns >= valid are padding tokens (last tile of a ragged count)
+        if (valid < 64) {
+#pragma unroll
+          for (int i = 0; i < 64; ++i)
+            if (i >= valid) sv[i] = 0xff800000u;       // -inf -> p = 0
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {                 // in place: sv[i] <- packed (p[2i], p[2i+1])
+          const float x0 = __uint_as_float(sv[2 * i]), x1 = __uint_as_float(sv[2 * i + 1]);
+          const float p0 = exp_on_fma<kPoly>(2 * i) ? exp2_poly(x0) : ex2(x0);
+          const float p1 = exp_on_fma<kPoly>(2 * i + 1) ? exp2_poly(x1) : ex2(x1);
+          l0 += p0; l1 += p1;
+          sv[i] = pack_h2(p0, p1);
+        }
+        HY3D_TICK(2)
+        if (j > 0) { mbar_wait(B.pvdone(a), pv_ph); pv_ph ^= 1; }   // PV(j-1) has consumed the previous P
+        HY3D_TICK(3)
+        HY3D_TMEM_ST32(t_p, sv);
+        tmem_wait_st();
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(B.pfull(a));
+        HY3D_TICK(4)
+      }
+      // ---- finalize: row sums of the two column halves through shared memory, O / l -> fp16 tile (q-tile, head) ----
+      float* ls = lsum + a * 256;
+      ls[hh * 128 + r] = l0 + l1;
+      asm volatile("bar.sync %0, 256;" ::"r"(1 + a) : "memory");
+      const float inv = 1.f / (ls[r] + ls[128 + r]);
+      mbar_wait(B.pvdone(a), pv_ph); pv_ph ^= 1;
+      fence_after_sync();
+      uint8_t* tile = g.O + ((size_t)qt * (g.split_out ? 3 : 1) * g.H + h) * TILE_BYTES;
+      {
+        uint32_t ov[32];
+        HY3D_TMEM_LD32(t_o, ov);
+        tmem_wait_ld();
+        float x[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(ov[i]) * inv;
+        if (g.split_out) {
+#pragma unroll
+          for (int c16 = 0; c16 < 4; ++c16)
+            store_t16_split(tile, tile + (size_t)g.H * TILE_BYTES, tile + (size_t)2 * g.H * TILE_BYTES, r, hh * 4 + c16, x + 8 * c16);
+        } else {
+#pragma unroll
+          for (int c16 = 0; c16 < 4; ++c16) store_t16_chunk(tile, r, hh * 4 + c16, x + 8 * c16);
+        }
+      }
+      fence_before_sync();
+      asm volatile("bar.sync %0, 256;" ::"r"(1 + a) : "memory");   // ls[] is reused by the next item
+      HY3D_TICK(5)
+      if constexpr (kTimers) {
+        if (g.timers && lane == 0 && q == 0 && hh == 0 && blockIdx.x == 0) {
+#pragma unroll
+          for (int i = 0; i < 6; ++i) { atomicAdd(&g.timers[a * 8 + i], (unsigned long long)tk[i]); tk[i] = 0; }
+          atomicAdd(&g.timers[a * 8 + 7], (unsigned long long)nkv);
+        }
+      }
+    }
+#undef HY3D_TICK
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------
+// General case: online softmax with a running maximum, one thread per query row.
+// ------------------------------------------------------------------------------------------
+template <int kPoly>
+__global__ void __launch_bounds__(ATT_THREADS, 1) k_attn_tc(AttnTC g) {
+  constexpr float kLazy = 8.f;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  AttnBars B;
+  const uint32_t tmem = attn_setup(smem, B, 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int HP = g.H / 2, nitems = g.Pb * HP, nkv = g.nkv;
+
+  if (warp < 4) {
+    reg_dealloc<80>();
+    if ((warp & 1) == 0) attn_producer(g, B, smem, warp >> 1);
+    else attn_mma(g, B, smem, tmem, warp >> 1);
+  } else {
+    reg_alloc<200>();
+    const int a = (warp - 4) >> 2;
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t t_s = tmem + TM_S0 + a * 128 + ((uint32_t)(q * 32) << 16);
+    const uint32_t t_o = tmem + TM_O0 + a * 64 + ((uint32_t)(q * 32) << 16);
+    const uint32_t t_p = tmem + TM_P0 + a * 64 + ((uint32_t)(q * 32) << 16);
+    uint32_t sfull_ph = 0, pv_ph = 0;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+      const int qt = item / HP, h = (item % HP) * 2 + a;
+      const int ntok = g.group_ntok ? g.group_ntok[g.tile_group ? g.tile_group[qt] : 0] : g.ntok;
+      float m = -INFINITY, l = 0.f;
+      for (int j = 0; j < nkv; ++j) {
+        mbar_wait(B.sfull(a), sfull_ph); sfull_ph ^= 1;
+        fence_after_sync();
+        uint32_t sv[128];
+        HY3D_TMEM_LD32(t_s, sv); HY3D_TMEM_LD32(t_s + 32, (sv + 32));
+        HY3D_TMEM_LD32(t_s + 64, (sv + 64)); HY3D_TMEM_LD32(t_s + 96, (sv + 96));
+        tmem_wait_ld();
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(B.sempty(a));
+        const int valid = ntok - j * 128;              // columns >= valid are padding tokens
+        if (valid < 128) {                             // only the last tile of a ragged token count
+#pragma unroll
+          for (int i = 0; i < 128; ++i)
+            if (i >= valid) sv[i] = 0xff800000u;       // -inf
+        }
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // 4 independent max chains (3-input FMNMX)
+#pragma unroll
+        for (int i = 0; i < 128; i += 8) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            mx4[u] = fmaxf(mx4[u], fmaxf(__uint_as_float(sv[i + 2 * u]), __uint_as_float(sv[i + 2 * u + 1])));
+        }
+        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+        bool need = false;
+        float m_new = m;
+        if (j == 0) { m_new = mx; }
+        else if (mx > m + kLazy) { m_new = mx; need = true; }   // lazy rescale: keep the old max while p <= 2^kLazy
+        // PV(j-1) must be complete before O is rescaled or the single P buffer is overwritten.  The
+        // rescale is rare (lazy threshold): normally the wait is deferred until this tile's
+        // probabilities sit packed in registers, so the MMA has the whole exp phase to finish.
+        bool waited = (j == 0);
+        if (j > 0 && __any_sync(0xffffffffu, need)) {
+          mbar_wait(B.pvdone(a), pv_ph); pv_ph ^= 1; waited = true;
+          fence_after_sync();
+          const float sc = need ? ex2(m - m_new) : 1.f;
+          l *= sc;
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            uint32_t ov[32];
+            HY3D_TMEM_LD32(t_o + c * 32, ov);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * sc);
+            HY3D_TMEM_ST32(t_o + c * 32, ov);
+          }
+          tmem_wait_st();
+        }
+        m = m_new;
+        float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {                       // in place: sv[i] <- packed (p[2i], p[2i+1])
+          const float x0 = __uint_as_float(sv[2 * i]) - m, x1 = __uint_as_float(sv[2 * i + 1]) - m;
+          const float p0 = exp_on_fma<kPoly>(2 * i) ? exp2_poly(x0) : ex2(x0);
+          const float p1 = exp_on_fma<kPoly>(2 * i + 1) ? exp2_poly(x1) : ex2(x1);
+          sum4[i & 1] += p0; sum4[2 + (i & 1)] += p1;
+          sv[i] = pack_h2(p0, p1);
+        }
+        l += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
+        if (!waited) { mbar_wait(B.pvdone(a), pv_ph); pv_ph ^= 1; }
+        HY3D_TMEM_ST32(t_p, sv); HY3D_TMEM_ST32(t_p + 32, (sv + 32));
+        tmem_wait_st();
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(B.pfull(a));
+      }
+      // ---- finalize: O / l -> fp16 tile (q-tile, head) ----
+      mbar_wait(B.pvdone(a), pv_ph); pv_ph ^= 1;
+      fence_after_sync();
+      const float inv = 1.f / l;
+      uint8_t* tile = g.O + ((size_t)qt * (g.split_out ? 3 : 1) * g.H + h) * TILE_BYTES;
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t ov[32];
+        HY3D_TMEM_LD32(t_o + c * 32, ov);
+        tmem_wait_ld();
+        float x[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(ov[i]) * inv;
+        if (g.split_out) {
+#pragma unroll
+          for (int c16 = 0; c16 < 4; ++c16)
+            store_t16_split(tile, tile + (size_t)g.H * TILE_BYTES, tile + (size_t)2 * g.H * TILE_BYTES, r, c * 4 + c16, x + 8 * c16);
+        } else {
+#pragma unroll
+          for (int c16 = 0; c16 < 4; ++c16) store_t16_chunk(tile, r, c * 4 + c16, x + 8 * c16);
+        }
+      }
+      fence_before_sync();
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 512);
+}

@@ -45,7 +45,11 @@ struct DecoderWeights {
   const __half *t_qp, *t_cq, *t_cproj, *t_fc, *t_mp;      // B tiles
   DevBuf fold;                        // LayerNorm-folded epilogue constants (decoder_tc.cu)
   const float *cs_q, *bb_q, *cs_fc, *bb_fc, *dotw, *c12;
-  const __half* t_cq3;                                    // c_q split [W_hi | W_hi | W_lo], K = 3W (fp32-grade q for KV selection)
+  const __half *t_ckv3, *t_lp3;                           // c_kv (ln_2 folded, [k | v] rows) and latents_proj, 3-term split
+  const float *cs_kv, *bb_kv;
+  const __half* t_cq3;
+  float attn_bound = 0.f;              // upper bound of |q.k| scale log2e from the q/k norm weights (inf without qk_norm)
+  bool attn_fast = false;              // bound <= 14: the attention kernel without a running maximum is exact (attention_tc.cuh)                                    // c_q split [W_hi | W_hi | W_lo], K = 3W (fp32-grade q for KV selection)
 };
 
 struct KVState {
@@ -73,6 +77,7 @@ struct TransformerState {
   DevBuf tc;                          // fp16 B16 images, 3-term split: post_kl, per layer c_qkv (LN-folded, rows permuted), c_proj, c_fc (LN-folded), mlp.c_proj
   DevBuf f32;                         // per layer: cs_qkv, bb_qkv, b_proj, cs_fc, bb_fc, b_proj2, q/k norm; post_kl bias
   std::vector<const uint8_t*> t_qkv, t_proj, t_fc, t_proj2;
+  std::vector<int> attn_fast;         // per layer: bounded attention scores (see DecoderWeights::attn_fast)
   std::vector<const float*> cs_qkv, bb_qkv, b_proj, cs_fc, bb_fc, b_proj2, qn_w, qn_b, kn_w, kn_b;
   const uint8_t* t_postkl = nullptr;
   const float* b_postkl = nullptr;
@@ -117,8 +122,9 @@ struct hy3d_ctx {
   void* pinned = nullptr;             // small pinned host buffer for read-backs
   Prof prof;
   // diagnostics: per-stage activations of the last decoded chunk (hy3d_debug_retain / hy3d_debug_fetch)
-  int attn_poly = 0;                  // of every 8 attention exponentials, how many run on the FMA pipe (HY3D_ATTN_POLY: 0,2,3,4,6)
+  int attn_poly = 1;                  // of every 8 attention exponentials, how many run on the FMA pipe (HY3D_ATTN_POLY: 0..4; bounded-score kernel)
   int debug_retain = 0;
+  int xbits = 0;                      // HY3D_DBG: experiment bits for tools/gpu_chain_bench.py (results are garbage when set)
   DevBuf dbg[8];
   int dbg_layout[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // 0 row-major fp32, 1 R32, 2 T16
   long long dbg_rows = 0;
@@ -185,6 +191,7 @@ int hy3d_decode_tc_groups(hy3d_ctx* ctx, const QuerySource& src, long long n, fl
 // q after q_norm (unscaled), ~fp32 accuracy via 3-term split fp16 tensor GEMMs: d_q row-major [ceil128(n), W]
 int hy3d_tc_sample_q(hy3d_ctx* ctx, const QuerySource& src, long long n, float* d_q);
 int hy3d_tc_prepare_kv(hy3d_ctx* ctx);
+int hy3d_tc_project_kv(hy3d_ctx* ctx, const float* d_latents, int M);   // tensor-path K/V projection (replaces simt prepare + tc prepare)
 int hy3d_simt_prepare_kv(hy3d_ctx* ctx, const float* d_latents, int M);
 
 __device__ __forceinline__ void hy3d_query_point(const QuerySource& s, long long q, float& x, float& y, float& z,

@@ -17,7 +17,8 @@
 //   k_gemm_tc<X0>   query_proj (3-term split fp16 = ~fp32)      -> R32 x0
 //   k_ln_tc         ln_1                                         -> T16
 //   k_gemm_tc<Q>    c_q, per-head q_norm, *scale*log2e           -> T16 q (k-block == head)
-//   k_attn_tc       softmax(q k^T) v, online softmax, 2 heads in flight per CTA -> T16
+//   k_attn_fast /   softmax(q k^T) v, 2 heads in flight per CTA (attention_tc.cuh)  -> T16
+//   k_attn_tc
 //   k_gemm_tc<RES>  c_proj + residual                            -> R32 x1
 //   k_ln_tc         ln_3                                         -> T16
 //   k_gemm_tc<GELU> c_fc + erf-GELU                              -> T16 h
@@ -28,6 +29,7 @@
 
 using namespace tc;
 
+__device__ unsigned long long hy3d_tm[32];   // phase clocks of the instrumented attention kernel (hy3d_debug_timers)
 namespace {
 
 constexpr int TILE_M = 128;
@@ -60,6 +62,9 @@ struct GemmTC {
   int split_out;         // Tcopy / Tout(GELU) written as [hi | lo | hi] (3 * N/64 k-blocks): operand of a 3-term split GEMM
   // EPI_QKV (latent transformer): output columns are [q (W) | k (W) | v (W)], head-contiguous
   uint8_t* Kout; uint8_t* Vout; const float* kn_w; const float* kn_b; int nkv; int Wq;
+  int part0;             // 0: columns [q | k | v] (latent transformer); 1: columns [k | v] (decoder c_kv)
+  float* K32; float* V32T; int Mtok;   // optional fp32 copies k [H, Mtok, 64], v^T [H, 64, Mtok] (FlashVDM selection); rows >= Mtok are written as zeros
+  int dbg;               // HY3D_DBG experiment bits: 1 no epilogue, 2 no MMA, 4 no epilogue stores
 };
 
 // merge S partial (mean, M2) pairs of n_p samples each -> (mean, rstd)
@@ -134,43 +139,46 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(GemmTC g) {
   const int ntiles = g.Mb * g.Nb;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int s = 0; uint32_t ph = 0;
-      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const int mb = t / g.Nb, nb = t % g.Nb;
-        const uint8_t* a = g.A + (size_t)mb * g.KB * TILE_BYTES;
-        const uint8_t* b = g.B + (size_t)nb * g.KB * BTILE_BYTES;
-        for (int kb = 0; kb < g.KB; ++kb) {
-          mbar_wait(EMPTY(s), ph ^ 1);
+    int s = 0; uint32_t ph = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      const int mb = t / g.Nb, nb = t % g.Nb;
+      const uint8_t* a = g.A + (size_t)mb * g.KB * TILE_BYTES;
+      const uint8_t* b = g.B + (size_t)nb * g.KB * BTILE_BYTES;
+      for (int kb = 0; kb < g.KB; ++kb) {
+        mbar_wait(EMPTY(s), ph ^ 1);
+        if (elect_one()) {
           mbar_arrive_expect_tx(FULL(s), TILE_BYTES + BTILE_BYTES);
           bulk_g2s(smem_u32(sA + s * TILE_BYTES), a + (size_t)kb * TILE_BYTES, TILE_BYTES, FULL(s));
           bulk_g2s(smem_u32(sB + s * BTILE_BYTES), b + (size_t)kb * BTILE_BYTES, BTILE_BYTES, FULL(s));
-          if (++s == GEMM_STAGES) { s = 0; ph ^= 1; }
         }
+        __syncwarp();
+        if (++s == GEMM_STAGES) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16(TILE_M, BN);
-      int s = 0; uint32_t ph = 0;
-      int it = 0;
-      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-        const int acc = it & 1;
-        const uint32_t aph = (it >> 1) & 1;
-        mbar_wait(TEMPTY(acc), aph ^ 1);
+    const uint32_t idesc = make_idesc_f16(TILE_M, BN);
+    int s = 0; uint32_t ph = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      mbar_wait(TEMPTY(acc), aph ^ 1);
+      fence_after_sync();
+      const uint32_t d = tmem + acc * BN;
+      for (int kb = 0; kb < g.KB; ++kb) {
+        mbar_wait(FULL(s), ph);
         fence_after_sync();
-        const uint32_t d = tmem + acc * BN;
-        for (int kb = 0; kb < g.KB; ++kb) {
-          mbar_wait(FULL(s), ph);
-          fence_after_sync();
-          const uint64_t ad = make_desc_sw128(smem_u32(sA + s * TILE_BYTES));
-          const uint64_t bd = make_desc_sw128(smem_u32(sB + s * BTILE_BYTES));
+        const uint64_t ad = make_desc_sw128(smem_u32(sA + s * TILE_BYTES));
+        const uint64_t bd = make_desc_sw128(smem_u32(sB + s * BTILE_BYTES));
+        if (elect_one()) {
+          if (!(g.dbg & 2))
 #pragma unroll
-          for (int k = 0; k < 4; ++k) mma_f16_ss(d, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
+            for (int k = 0; k < 4; ++k) mma_f16_ss(d, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
           mma_commit(EMPTY(s));
-          if (++s == GEMM_STAGES) { s = 0; ph ^= 1; }
+          if (kb == g.KB - 1) mma_commit(TFULL(acc));
         }
-        mma_commit(TFULL(acc));
+        __syncwarp();
+        if (++s == GEMM_STAGES) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp >= 4) {
@@ -185,6 +193,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(GemmTC g) {
       const uint32_t aph = (it >> 1) & 1;
       mbar_wait(TFULL(acc), aph);
       fence_after_sync();
+      if (g.dbg & 1) { fence_before_sync(); __syncwarp(); if (lane == 0) mbar_arrive(TEMPTY(acc)); continue; }
       const uint32_t trow = tmem + acc * BN + ((uint32_t)(q * 32) << 16);
       const int col0 = nb * BN + half * (BN / 2);          // first global column of this warp's half
       float ln_mean = 0.f, ln_rstd = 1.f;
@@ -217,8 +226,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(GemmTC g) {
               x[4 * i4] = a0 + bv.x; x[4 * i4 + 1] = a1 + bv.y; x[4 * i4 + 2] = a2 + bv.z; x[4 * i4 + 3] = a3 + bv.w;
             }
           }
-          int part = 0;                                       // 0 q, 1 k, 2 v (EPI_QKV); q otherwise
-          if constexpr (EPI == EPI_QKV) part = c / g.Wq;
+          int part = 0, cpart = 0;                            // 0 q, 1 k, 2 v (EPI_QKV); q otherwise
+          if constexpr (EPI == EPI_QKV) { cpart = c / g.Wq; part = cpart + g.part0; }
           const float* nw = part == 1 ? g.kn_w : g.qn_w;
           const float* nb = part == 1 ? g.kn_b : g.qn_b;
           const float oscale = part == 0 ? g.qscale : 1.f;
@@ -248,7 +257,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(GemmTC g) {
 #pragma unroll
             for (int i4 = 0; i4 < 16; ++i4) o[i4] = make_float4(x[4 * i4], x[4 * i4 + 1], x[4 * i4 + 2], x[4 * i4 + 3]);
           } else if constexpr (EPI == EPI_QKV) {
-            const int h = (c - part * g.Wq) >> 6;
+            const int h = (c - cpart * g.Wq) >> 6;
+            const int row = mb * TILE_M + r;
+            if (g.Mtok > 0 && row >= g.Mtok) {                // padding tokens: exact zeros
+#pragma unroll
+              for (int i = 0; i < 64; ++i) x[i] = 0.f;
+            }
+            if (part == 1 && g.K32 && row < g.Mtok) {
+              float4* o = reinterpret_cast<float4*>(g.K32 + ((size_t)h * g.Mtok + row) * 64);
+#pragma unroll
+              for (int i4 = 0; i4 < 16; ++i4) o[i4] = make_float4(x[4 * i4], x[4 * i4 + 1], x[4 * i4 + 2], x[4 * i4 + 3]);
+            }
+            if (part == 2 && g.V32T && row < g.Mtok) {
+              float* o = g.V32T + (size_t)h * 64 * g.Mtok + row;
+#pragma unroll
+              for (int d = 0; d < 64; ++d) o[(size_t)d * g.Mtok] = x[d];
+            }
             if (part == 0) {                                  // q: T16 [Mb][H], k-block == head
               uint8_t* tile = g.Tout + ((size_t)mb * (g.Wq / 64) + h) * TILE_BYTES;
 #pragma unroll
@@ -263,10 +287,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(GemmTC g) {
 #pragma unroll
               for (int d = 0; d < 64; ++d) *reinterpret_cast<__half*>(tile + sw128_off(d, c16)) = __float2half_rn(x[d]);
             }
-          } else {
+          } else if (!(g.dbg & 4)) {
             uint8_t* tile = g.Tout + ((size_t)mb * (g.N / 64) + (c >> 6)) * TILE_BYTES;
 #pragma unroll
             for (int c16 = 0; c16 < 8; ++c16) store_t16_chunk(tile, r, c16, x + 8 * c16);
+          } else {
+            float acc_ = 0.f;
+#pragma unroll
+            for (int i = 0; i < 64; ++i) acc_ += x[i];
+            if (acc_ == 123.456f) g.Tout[0] = 1;
           }
         }
       } else {
@@ -306,9 +335,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(GemmTC g) {
 #pragma unroll
               for (int c16 = 0; c16 < 4; ++c16)
                 store_t16_split(tile, tile + (size_t)KBn * TILE_BYTES, tile + (size_t)2 * KBn * TILE_BYTES, r, cbase + c16, x + 8 * c16);
-            } else {
+            } else if (!(g.dbg & 4)) {
 #pragma unroll
               for (int c16 = 0; c16 < 4; ++c16) store_t16_chunk(tile, r, cbase + c16, x + 8 * c16);
+            } else {
+              float acc_ = 0.f;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) acc_ += x[i];
+              if (acc_ == 123.456f) g.Tout[0] = 1;
             }
           } else {
             // R32: [mb][c/4][row][4]
@@ -322,9 +356,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(GemmTC g) {
                 o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
                 x[4 * i4] = o.x; x[4 * i4 + 1] = o.y; x[4 * i4 + 2] = o.z; x[4 * i4 + 3] = o.w;
               }
-              if (g.Rout) reinterpret_cast<float4*>(g.Rout)[idx] = o;
+              if (g.Rout && !(g.dbg & 4)) reinterpret_cast<float4*>(g.Rout)[idx] = o;
             }
-            if (g.Tcopy) {
+            if (g.Tcopy && !(g.dbg & 4)) {
               const int KBn = g.N / 64;
               uint8_t* tile = g.Tcopy + ((size_t)mb * (g.split_out ? 3 : 1) * KBn + (c >> 6)) * TILE_BYTES;
               const int cbase = (c & 63) >> 3;
@@ -380,270 +414,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(GemmTC g) {
 
 constexpr size_t GEMM_SMEM = 1024 + GEMM_STAGES * (TILE_BYTES + BTILE_BYTES) + 256;
 
-// ------------------------------------------------------------------------------------------
-// Attention: per CTA one 128-query tile, two heads in flight (softmax warpgroup per head).
-// ------------------------------------------------------------------------------------------
-constexpr int ATT_THREADS = 384;           // per head stream a in {0,1}: warp 2a producer, warp 2a+1 MMA issuer, warps 4+4a.. softmax
-constexpr int ATT_SLOTS = 3;               // K / V^T ring per stream, 16 KB each
-constexpr int TM_S0 = 0, TM_O0 = 256;      // TMEM columns: S[a] at a*128, O[a] at 256 + a*64
-
-struct AttnTC {
-  const uint8_t* Q;      // T16 [Pb][H]
-  const uint8_t* K;      // [group][H][nkv][16 KB]
-  const uint8_t* V;      // [group][H][nkv][16 KB]
-  uint8_t* O;            // T16 [Pb][H]
-  const int* tile_group; // per q-tile KV group or null
-  const int* group_ntok; // valid tokens per group or null
-  int Pb, H, nkv, ntok;  // nkv = tiles per (group, head); ntok = valid tokens when group_ntok == null
-  unsigned stagger_ns;   // start delay of head stream 1
-  int split_out;         // O written as [hi | lo | hi] over 3H k-blocks (operand of a 3-term split GEMM)
-};
-
-// Two fully independent head streams per CTA (own producer thread, MMA-issuing thread, softmax
-// warpgroup, K/V ring and barriers), so that neither stream's waits block the other: the tensor
-// pipe interleaves their MMAs, the SFU-bound softmax phases drift apart instead of marching in step.
-// exp2 on the FMA/ALU pipes (Cody-Waite split + degree-3 minimax on [-0.5, 0.5], max rel. error 1.6e-4,
-// below the fp16 rounding of the stored probability): the SFU sustains only ~8 ex2/clk/SM on this part, so a
-// fraction kPoly/8 of the exponentials is taken off it (the FlashAttention-4 recipe).
-__device__ __forceinline__ float exp2_poly(float x) {
-  x = fmaxf(x, -126.f);
-  const float t = x + 12582912.f;                 // round to nearest integer in the low mantissa bits
-  const float f = x - (t - 12582912.f);
-  float p = fmaf(5.360121652e-02f, f, 2.423726171e-01f);
-  p = fmaf(p, f, 6.935024858e-01f);
-  p = fmaf(p, f, 9.999481440e-01f);
-  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
-}
-
-template <int kPoly>
-__global__ void __launch_bounds__(ATT_THREADS, 1) k_attn_tc(AttnTC g) {
-  constexpr float kLazy = 8.f;
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                                   // [2][16 KB]
-  uint8_t* sP = smem + 2 * TILE_BYTES;                  // [2][32 KB]
-  uint8_t* sKV = smem + 2 * TILE_BYTES + 2 * 2 * TILE_BYTES;   // [2][SLOTS][16 KB]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + 2 * ATT_SLOTS * TILE_BYTES);
-  const uint32_t bar0 = smem_u32(bars);
-  constexpr int NB = 2 * ATT_SLOTS + 6;                 // barriers per stream
-  auto KVFULL = [&](int a, int s) { return bar0 + 8u * (a * NB + s); };
-  auto KVEMPTY = [&](int a, int s) { return bar0 + 8u * (a * NB + ATT_SLOTS + s); };
-  auto QFULL = [&](int a) { return bar0 + 8u * (a * NB + 2 * ATT_SLOTS); };
-  auto QEMPTY = [&](int a) { return bar0 + 8u * (a * NB + 2 * ATT_SLOTS + 1); };
-  auto SFULL = [&](int a) { return bar0 + 8u * (a * NB + 2 * ATT_SLOTS + 2); };
-  auto SEMPTY = [&](int a) { return bar0 + 8u * (a * NB + 2 * ATT_SLOTS + 3); };
-  auto PFULL = [&](int a) { return bar0 + 8u * (a * NB + 2 * ATT_SLOTS + 4); };
-  auto PVDONE = [&](int a) { return bar0 + 8u * (a * NB + 2 * ATT_SLOTS + 5); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NB);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
-    for (int a = 0; a < 2; ++a) {
-      for (int s = 0; s < ATT_SLOTS; ++s) { mbar_init(KVFULL(a, s), 1); mbar_init(KVEMPTY(a, s), 1); }
-      mbar_init(QFULL(a), 1); mbar_init(QEMPTY(a), 1);
-      mbar_init(SFULL(a), 1); mbar_init(SEMPTY(a), 4); mbar_init(PFULL(a), 4); mbar_init(PVDONE(a), 1);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 2) { tmem_alloc(smem_u32(tmem_slot), 512); tmem_relinquish(); }
-  fence_before_sync();
-  __syncthreads();
-  fence_after_sync();
-  const uint32_t tmem = *tmem_slot;
-  const int HP = g.H / 2;
-  const int nitems = g.Pb * HP;
-  const int nkv = g.nkv;
-
-  if (warp < 4) {
-    reg_dealloc<80>();
-    const int a = warp >> 1;                            // head stream
-    if ((warp & 1) == 0 && lane == 0) {
-      // ---------------- producer of stream a: Q, K(0), then per j: K(j+1), V(j) ----------------
-      int s = 0; uint32_t ph = 0; uint32_t qph = 0;
-      uint8_t* ring = sKV + a * ATT_SLOTS * TILE_BYTES;
-      auto push = [&](const uint8_t* src) {
-        mbar_wait(KVEMPTY(a, s), ph ^ 1);
-        mbar_arrive_expect_tx(KVFULL(a, s), TILE_BYTES);
-        bulk_g2s(smem_u32(ring + s * TILE_BYTES), src, TILE_BYTES, KVFULL(a, s));
-        if (++s == ATT_SLOTS) { s = 0; ph ^= 1; }
-      };
-      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-        const int qt = item / HP, h = (item % HP) * 2 + a;
-        const int grp = g.tile_group ? g.tile_group[qt] : 0;
-        mbar_wait(QEMPTY(a), qph ^ 1);
-        mbar_arrive_expect_tx(QFULL(a), TILE_BYTES);
-        bulk_g2s(smem_u32(sQ + a * TILE_BYTES), g.Q + ((size_t)qt * g.H + h) * TILE_BYTES, TILE_BYTES, QFULL(a));
-        qph ^= 1;
-        const uint8_t* kb = g.K + ((size_t)grp * g.H + h) * nkv * TILE_BYTES;
-        const uint8_t* vb = g.V + ((size_t)grp * g.H + h) * nkv * TILE_BYTES;
-        push(kb);
-        for (int j = 0; j < nkv; ++j) {
-          if (j + 1 < nkv) push(kb + (size_t)(j + 1) * TILE_BYTES);
-          push(vb + (size_t)j * TILE_BYTES);
-        }
-      }
-    } else if ((warp & 1) == 1 && lane == 0) {
-      // ---------------- MMA issuer of stream a ----------------
-      const uint32_t idesc_s = make_idesc_f16(128, 128);
-      const uint32_t idesc_o = make_idesc_f16(128, 64);
-      int s = 0; uint32_t ph = 0; uint32_t qph = 0;
-      uint32_t sph = 0, pph = 0;                        // phases of SEMPTY / PFULL waits
-      uint8_t* ring = sKV + a * ATT_SLOTS * TILE_BYTES;
-      auto issue_s = [&]() {
-        mbar_wait(KVFULL(a, s), ph);
-        mbar_wait(SEMPTY(a), sph ^ 1); sph ^= 1;
-        fence_after_sync();
-        const uint64_t ad = make_desc_sw128(smem_u32(sQ + a * TILE_BYTES));
-        const uint64_t bd = make_desc_sw128(smem_u32(ring + s * TILE_BYTES));
-#pragma unroll
-        for (int k = 0; k < 4; ++k) mma_f16_ss(tmem + TM_S0 + a * 128, ad + 2 * k, bd + 2 * k, idesc_s, k != 0);
-        mma_commit(KVEMPTY(a, s));
-        mma_commit(SFULL(a));
-        if (++s == ATT_SLOTS) { s = 0; ph ^= 1; }
-      };
-      auto issue_pv = [&](int j) {
-        mbar_wait(KVFULL(a, s), ph);
-        mbar_wait(PFULL(a), pph); pph ^= 1;
-        fence_after_sync();
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint64_t ad = make_desc_sw128(smem_u32(sP + a * 2 * TILE_BYTES + (k >> 2) * TILE_BYTES)) + 2 * (k & 3);
-          const uint64_t bd = make_desc_sw128(smem_u32(ring + s * TILE_BYTES + (k >> 2) * (TILE_BYTES / 2))) + 2 * (k & 3);
-          mma_f16_ss(tmem + TM_O0 + a * 64, ad, bd, idesc_o, (j | k) != 0);
-        }
-        mma_commit(KVEMPTY(a, s));
-        mma_commit(PVDONE(a));
-        if (++s == ATT_SLOTS) { s = 0; ph ^= 1; }
-      };
-      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-        mbar_wait(QFULL(a), qph); qph ^= 1;
-        fence_after_sync();
-        issue_s();
-        for (int j = 0; j < nkv; ++j) {
-          if (j + 1 < nkv) issue_s();
-          else mma_commit(QEMPTY(a));                  // all S MMAs of this item issued: Q may be refilled once they finish
-          issue_pv(j);
-        }
-      }
-    }
-  } else {
-    reg_alloc<200>();
-    // ---------------- softmax warpgroups: a = head slot, one thread per query row ----------------
-    const int a = (warp - 4) >> 2;
-    const int q = warp & 3;
-    const int r = q * 32 + lane;
-    const uint32_t t_s = tmem + TM_S0 + a * 128 + ((uint32_t)(q * 32) << 16);
-    const uint32_t t_o = tmem + TM_O0 + a * 64 + ((uint32_t)(q * 32) << 16);
-    uint8_t* sPa = sP + a * 2 * TILE_BYTES;
-    uint32_t sfull_ph = 0, pv_ph = 0;
-    // Both streams are SFU-bound in their exp phase and idle the SFU otherwise: start stream 1 half a tile
-    // period late so that one stream's exp phase overlaps the other's load / max / wait phases.
-    if (a == 1 && g.stagger_ns) __nanosleep(g.stagger_ns);
-    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-      const int qt = item / HP, h = (item % HP) * 2 + a;
-      const int ntok = g.group_ntok ? g.group_ntok[g.tile_group ? g.tile_group[qt] : 0] : g.ntok;
-      float m = -INFINITY, l = 0.f;
-      for (int j = 0; j < nkv; ++j) {
-        mbar_wait(SFULL(a), sfull_ph); sfull_ph ^= 1;
-        fence_after_sync();
-        uint32_t sv[128];
-        HY3D_TMEM_LD32(t_s, sv); HY3D_TMEM_LD32(t_s + 32, (sv + 32));
-        HY3D_TMEM_LD32(t_s + 64, (sv + 64)); HY3D_TMEM_LD32(t_s + 96, (sv + 96));
-        tmem_wait_ld();
-        fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(SEMPTY(a));
-        const int valid = ntok - j * 128;              // columns >= valid are padding tokens
-        if (valid < 128) {                             // only the last tile of a ragged token count
-#pragma unroll
-          for (int i = 0; i < 128; ++i)
-            if (i >= valid) sv[i] = 0xff800000u;       // -inf
-        }
-        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // 4 independent max chains (3-input FMNMX)
-#pragma unroll
-        for (int i = 0; i < 128; i += 8) {
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-            mx4[u] = fmaxf(mx4[u], fmaxf(__uint_as_float(sv[i + 2 * u]), __uint_as_float(sv[i + 2 * u + 1])));
-        }
-        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-        bool need = false;
-        float m_new = m;
-        if (j == 0) { m_new = mx; }
-        else if (mx > m + kLazy) { m_new = mx; need = true; }   // lazy rescale: keep the old max while p <= 2^kLazy
-        // PV(j-1) must be complete before O is rescaled or the single P buffer is overwritten.  The
-        // rescale is rare (lazy threshold): normally the wait is deferred until this tile's
-        // probabilities sit packed in registers, so the MMA has the whole exp phase to finish.
-        bool waited = (j == 0);
-        if (j > 0 && __any_sync(0xffffffffu, need)) {
-          mbar_wait(PVDONE(a), pv_ph); pv_ph ^= 1; waited = true;
-          fence_after_sync();
-          const float sc = need ? ex2(m - m_new) : 1.f;
-          l *= sc;
-#pragma unroll 1
-          for (int c = 0; c < 2; ++c) {
-            uint32_t ov[32];
-            HY3D_TMEM_LD32(t_o + c * 32, ov);
-            tmem_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * sc);
-            HY3D_TMEM_ST32(t_o + c * 32, ov);
-          }
-          tmem_wait_st();
-        }
-        m = m_new;
-        float sum4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int i = 0; i < 64; ++i) {                       // in place: sv[i] <- packed (p[2i], p[2i+1])
-          constexpr unsigned kMask = kPoly == 0 ? 0x00u : kPoly == 2 ? 0x22u : kPoly == 3 ? 0x52u : kPoly == 4 ? 0xAAu : 0xEEu;
-          const float x0 = __uint_as_float(sv[2 * i]) - m, x1 = __uint_as_float(sv[2 * i + 1]) - m;
-          const float p0 = ((kMask >> ((2 * i) & 7)) & 1u) ? exp2_poly(x0) : ex2(x0);
-          const float p1 = ((kMask >> ((2 * i + 1) & 7)) & 1u) ? exp2_poly(x1) : ex2(x1);
-          sum4[i & 1] += p0; sum4[2 + (i & 1)] += p1;
-          sv[i] = pack_h2(p0, p1);
-        }
-        l += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
-        if (!waited) { mbar_wait(PVDONE(a), pv_ph); pv_ph ^= 1; }
-#pragma unroll
-        for (int c16 = 0; c16 < 16; ++c16)
-          *reinterpret_cast<uint4*>(sPa + (c16 >> 3) * TILE_BYTES + sw128_off(r, c16 & 7)) =
-              make_uint4(sv[4 * c16], sv[4 * c16 + 1], sv[4 * c16 + 2], sv[4 * c16 + 3]);
-        fence_proxy_async_smem();
-        fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(PFULL(a));
-      }
-      // ---- finalize: O / l -> fp16 tile (q-tile, head) ----
-      mbar_wait(PVDONE(a), pv_ph); pv_ph ^= 1;
-      fence_after_sync();
-      const float inv = 1.f / l;
-      uint8_t* tile = g.O + ((size_t)qt * (g.split_out ? 3 : 1) * g.H + h) * TILE_BYTES;
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        uint32_t ov[32];
-        HY3D_TMEM_LD32(t_o + c * 32, ov);
-        tmem_wait_ld();
-        float x[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(ov[i]) * inv;
-        if (g.split_out) {
-#pragma unroll
-          for (int c16 = 0; c16 < 4; ++c16)
-            store_t16_split(tile, tile + (size_t)g.H * TILE_BYTES, tile + (size_t)2 * g.H * TILE_BYTES, r, c * 4 + c16, x + 8 * c16);
-        } else {
-#pragma unroll
-          for (int c16 = 0; c16 < 4; ++c16) store_t16_chunk(tile, r, c * 4 + c16, x + 8 * c16);
-        }
-      }
-      fence_before_sync();
-    }
-  }
-  fence_before_sync();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem, 512);
-}
-
-constexpr size_t ATT_SMEM = 1024 + (2 + 4 + 2 * ATT_SLOTS) * TILE_BYTES + 512;
+#include "attention_tc.cuh"
 
 // ------------------------------------------------------------------------------------------
 // Small HBM-bound stages around the GEMMs
@@ -813,15 +584,16 @@ __global__ void __launch_bounds__(256) k_head_consts(const float* __restrict__ g
 
 // LayerNorm fold: Wf[j][k] = gamma[k] * W[j][k];  cs[j] = sum_k fp16(Wf[j][k]);  bb[j] = sum_k beta[k] W[j][k] + bias[j]
 // (one warp per output row j)
-// permH > 0: source rows are [head][q|k|v][64] (c_qkv, attention_blocks.py:318-321), output rows [q | k | v] head-contiguous.
+// permH > 0: source rows are [head][q|k|v][64] (c_qkv, attention_blocks.py:318-321; parts = 3) or [head][k|v][64] (c_kv, :205-208;
+// parts = 2), output rows [q | k | v] / [k | v] head-contiguous.
 // exact_cs: column sums of the unrounded folded weight (3-term split GEMMs) instead of its fp16 rounding.
 __global__ void k_fold_ln(const float* __restrict__ Wsrc, const float* __restrict__ gam, const float* __restrict__ bet,
                           const float* __restrict__ bias, int N, int K, float* __restrict__ Wf, float* __restrict__ cs,
-                          float* __restrict__ bb, int permH, int exact_cs) {
+                          float* __restrict__ bb, int permH, int exact_cs, int parts = 3) {
   const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (j >= N) return;
   int jd = j;
-  if (permH) { const int h = j / 192, p = (j % 192) / 64, d = j % 64; jd = p * (permH * 64) + h * 64 + d; }
+  if (permH) { const int hs = 64 * parts, h = j / hs, p = (j % hs) / 64, d = j % 64; jd = p * (permH * 64) + h * 64 + d; }
   float a = 0.f, b = 0.f;
   for (int k = lane; k < K; k += 32) {
     const float w = Wsrc[(size_t)j * K + k];
@@ -900,8 +672,64 @@ int launch_gemm(hy3d_ctx* ctx, const GemmTC& g, int fam) {
   int tiles = g.Mb * g.Nb;
   int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
   HY3D_PROF(ctx, fam);
-  k_gemm_tc<EPI><<<grid, GEMM_THREADS, GEMM_SMEM, ctx->stream>>>(g);
+  GemmTC gd = g; gd.dbg = ctx->xbits & 7;
+  k_gemm_tc<EPI><<<grid, GEMM_THREADS, GEMM_SMEM, ctx->stream>>>(gd);
   HY3D_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+// Attention launch: the bounded-score kernel when `fast` (see attention_tc.cuh), else the online-softmax kernel.
+// ctx->attn_poly = how many of every 8 exponentials run on the FMA pipe; ctx->xbits & 0x20 forces the general kernel,
+// 0x40 runs the instrumented fast kernel (hy3d_debug_timers).
+template <class K>
+int launch_attn_kernel(hy3d_ctx* ctx, K kern, const AttnTC& a, int threads) {
+  HY3D_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
+  const int items = a.Pb * (a.H / 2);
+  const int grid = items < ctx->num_sms ? items : ctx->num_sms;
+  kern<<<grid, threads, ATT_SMEM, ctx->stream>>>(a);
+  return 0;
+}
+int launch_attn(hy3d_ctx* ctx, AttnTC a, bool fast, int fam) {
+  HY3D_PROF(ctx, fam);
+  if (ctx->xbits & 0x20) fast = false;
+  int rc = 0;
+  if (fast) {
+    if (ctx->xbits & 0x40) {
+      void* tm = nullptr;
+      HY3D_CUDA(ctx, cudaGetSymbolAddress(&tm, hy3d_tm));
+      a.timers = reinterpret_cast<unsigned long long*>(tm);
+      rc = launch_attn_kernel(ctx, k_attn_fast<0, true>, a, ATT_FAST_THREADS);
+    } else {
+      switch (ctx->attn_poly) {
+        case 1: rc = launch_attn_kernel(ctx, k_attn_fast<1, false>, a, ATT_FAST_THREADS); break;
+        case 2: rc = launch_attn_kernel(ctx, k_attn_fast<2, false>, a, ATT_FAST_THREADS); break;
+        case 3: rc = launch_attn_kernel(ctx, k_attn_fast<3, false>, a, ATT_FAST_THREADS); break;
+        case 4: rc = launch_attn_kernel(ctx, k_attn_fast<4, false>, a, ATT_FAST_THREADS); break;
+        default: rc = launch_attn_kernel(ctx, k_attn_fast<0, false>, a, ATT_FAST_THREADS); break;
+      }
+    }
+  } else {
+    rc = launch_attn_kernel(ctx, k_attn_tc<0>, a, ATT_THREADS);
+  }
+  if (rc) return rc;
+  HY3D_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+// Upper bound of |q . k| * scale * log2e for LayerNorm-ed q and k (over d = 64 head dims, affine (w, b)):
+// ||w * xhat + b|| <= sqrt(d) * max|w| + ||b||.  Reads the 4 x 64 norm parameters back once, at weight-load time.
+int attn_score_bound(hy3d_ctx* ctx, const float* qw, const float* qb, const float* kw, const float* kb, float* bound) {
+  float h[4][64];
+  const float* src[4] = {qw, qb, kw, kb};
+  HY3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < 4; ++i) HY3D_CUDA(ctx, cudaMemcpy(h[i], src[i], sizeof(float) * 64, cudaMemcpyDeviceToHost));
+  float n[2];
+  for (int i = 0; i < 2; ++i) {
+    float mw = 0.f, nb = 0.f;
+    for (int d = 0; d < 64; ++d) { mw = fmaxf(mw, fabsf(h[2 * i][d])); nb += h[2 * i + 1][d] * h[2 * i + 1][d]; }
+    n[i] = 8.f * mw + sqrtf(nb);
+  }
+  *bound = n[0] * n[1] * 0.125f * LOG2E;
   return 0;
 }
 
@@ -920,7 +748,8 @@ int hy3d_tc_prepare_weights(hy3d_ctx* ctx) {
   }
   const size_t W = w.W, R = w.R;
   const size_t n_qp = W * 192, n_cq = W * W, n_cp = W * W, n_fc = R * W * W, n_mp = R * W * W, n_cq3 = 3 * W * W;
-  HY3D_CUDA(ctx, w.tc.reserve((n_qp + n_cq + n_cp + n_fc + n_mp + n_cq3) * 2));
+  const size_t n_ckv3 = 2 * W * 3 * W, n_lp3 = w.has_latents_proj ? W * 3 * (size_t)w.LW : 0;
+  HY3D_CUDA(ctx, w.tc.reserve((n_qp + n_cq + n_cp + n_fc + n_mp + n_cq3 + n_ckv3 + n_lp3) * 2));
   __half* base = w.tc.as<__half>();
   __half* p_qp = base; __half* p_cq = p_qp + n_qp; __half* p_cp = p_cq + n_cq; __half* p_fc = p_cp + n_cp; __half* p_mp = p_fc + n_fc;
   auto build = [&](const float* src, int N, int K, int ldw, int mode, __half* dst) -> int {
@@ -930,7 +759,7 @@ int hy3d_tc_prepare_weights(hy3d_ctx* ctx) {
     return 0;
   };
   // ln_1 folded into c_q, ln_3 into c_fc, ln_post into the head (see GemmTC)
-  HY3D_CUDA(ctx, w.fold.reserve((W + W + R * W + R * W + W + 64) * sizeof(float)));
+  HY3D_CUDA(ctx, w.fold.reserve((W + W + R * W + R * W + W + 64 + 4 * W) * sizeof(float)));
   HY3D_CUDA(ctx, ctx->ws[10].reserve(R * W * W * sizeof(float)));
   float* fb = w.fold.as<float>();
   float* cs_q = fb; float* bb_q = cs_q + W; float* cs_fc = bb_q + W; float* bb_fc = cs_fc + R * W; float* dotw = bb_fc + R * W; float* c12 = dotw + W;
@@ -950,6 +779,26 @@ int hy3d_tc_prepare_weights(hy3d_ctx* ctx) {
   __half* p_cq3 = p_mp + n_mp;
   if (int rc = build(w.cq_w, (int)W, (int)(3 * W), (int)W, 2, p_cq3)) return rc;
   w.t_qp = p_qp; w.t_cq = p_cq; w.t_cproj = p_cp; w.t_fc = p_fc; w.t_mp = p_mp; w.t_cq3 = p_cq3;
+  w.attn_bound = INFINITY; w.attn_fast = false;
+  if (w.qk_norm) {
+    if (int rc = attn_score_bound(ctx, w.qn_w, w.qn_b, w.kn_w, w.kn_b, &w.attn_bound)) return rc;
+    w.attn_fast = w.attn_bound <= ATT_FAST_BOUND;
+  }
+  if (getenv("HY3D_VERBOSE")) fprintf(stderr, "[hy3dgeo] decoder attention score bound %.3f -> %s kernel\n", w.attn_bound, w.attn_fast ? "bounded-score" : "online-softmax");
+  // per-latent K/V projection on the tensor path (hy3d_tc_project_kv): ln_2 folded into c_kv, rows permuted
+  // [head][k|v][64] -> [k | v], 3-term split (fp32-grade: K/V feed every query and the FlashVDM token selection)
+  w.t_ckv3 = nullptr; w.t_lp3 = nullptr;
+  if (w.LW % 64 == 0 && (!w.has_latents_proj || w.LW % 64 == 0)) {
+    float* cs_kv = c12 + 64; float* bb_kv = cs_kv + 2 * W;
+    __half* p_ckv3 = p_cq3 + n_cq3; __half* p_lp3 = p_ckv3 + n_ckv3;
+    k_fold_ln<<<(unsigned)((2 * W + 7) / 8), 256, 0, ctx->stream>>>(w.ckv_w, w.ln2_w, w.ln2_b, w.has_ckv_b ? w.ckv_b : nullptr, (int)(2 * W),
+                                                                    (int)W, Wf, cs_kv, bb_kv, w.H, 1, 2);
+    HY3D_LAUNCH_CHECK(ctx);
+    if (int rc = build(Wf, (int)(2 * W), (int)(3 * W), (int)W, 2, p_ckv3)) return rc;
+    if (w.has_latents_proj)
+      if (int rc = build(w.lp_w, (int)W, (int)(3 * w.LW), (int)w.LW, 2, p_lp3)) return rc;
+    w.t_ckv3 = p_ckv3; w.t_lp3 = w.has_latents_proj ? p_lp3 : nullptr; w.cs_kv = cs_kv; w.bb_kv = bb_kv;
+  }
   return 0;
 }
 
@@ -966,6 +815,93 @@ int hy3d_tc_prepare_kv(hy3d_ctx* ctx) {
   k_build_kv<<<(unsigned)ceil_div64(total, 256), 256, 0, ctx->stream>>>(kv.k32.as<float>(), kv.v32.as<float>(), w.H, kv.M, nkv,
                                                                         kv.ktile.as<uint8_t>(), kv.vtile.as<uint8_t>());
   HY3D_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+namespace {
+// fp32 rows [M, K] -> T16 split [hi | lo | hi]
+__global__ void k_rows_to_t16_split(const float* __restrict__ src, int M, int K, uint8_t* __restrict__ T) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // one 8-element chunk per thread
+  const int c8n = K / 8;
+  const long long rows_p = (long long)((M + 127) / 128) * 128;
+  if (t >= rows_p * c8n) return;
+  const int c8 = (int)(t % c8n); const long long row = t / c8n;
+  const int KBn = K / 64;
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = row < M ? src[row * K + c8 * 8 + i] : 0.f;
+  uint8_t* t0 = T + ((size_t)(row / 128) * 3 * KBn + (c8 >> 3)) * TILE_BYTES;
+  store_t16_split(t0, t0 + (size_t)KBn * TILE_BYTES, t0 + (size_t)2 * KBn * TILE_BYTES, (int)(row % 128), c8 & 7, v);
+}
+
+}  // namespace
+
+namespace {
+// per-row (mean, M2) of fp32 rows [M, K] in the slot format of GemmTC::st_in: slot s covers columns [128 s, 128 s + 128)
+__global__ void k_row_slot_stats(const float* __restrict__ src, int M, int K, float* __restrict__ st) {
+  const long long wi = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31, S = K / 128;
+  const long long rows_p = (long long)((M + 127) / 128) * 128;
+  if (wi >= rows_p * S) return;
+  const long long row = wi / S; const int slot = (int)(wi % S);
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (row < M) v = reinterpret_cast<const float4*>(src + row * K + slot * 128)[lane];
+  float sum = (v.x + v.y) + (v.z + v.w);
+  for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum * (1.f / 128.f);
+  const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
+  float m2 = (a * a + b * b) + (c * c + d * d);
+  for (int o = 16; o; o >>= 1) m2 += __shfl_xor_sync(0xffffffffu, m2, o);
+  if (lane == 0) { st[(row * S + slot) * 2] = mean; st[(row * S + slot) * 2 + 1] = m2; }
+}
+}  // namespace
+
+// K/V of one latent set on the tensor path (reference attention_blocks.py:487-488 latents_proj, :237/:291 ln_2, :257 c_kv,
+// :205-211 per-head split + k_norm): fp16 K / V^T tile images for the attention kernel plus fp32 copies for the FlashVDM
+// token selection, in two launches (three with latents_proj) instead of the fp32 SIMT GEMMs.
+int hy3d_tc_project_kv(hy3d_ctx* ctx, const float* d_latents, int M) {
+  DecoderWeights& w = ctx->w;
+  if (!w.t_qp || !w.t_ckv3) return hy3d_fail(ctx, HY3D_ERR_UNSUPPORTED, "tcgen05 K/V projection unavailable for this decoder shape");
+  KVState& kv = ctx->kv;
+  const int W = w.W, H = w.H, LW = w.LW;
+  const int Mb = (M + 127) / 128, nkv = Mb, S = 2 * (W / BN);
+  const size_t Mp = (size_t)Mb * 128;
+  HY3D_CUDA(ctx, kv.k32.reserve((size_t)H * M * 64 * 4));
+  HY3D_CUDA(ctx, kv.v32.reserve((size_t)H * M * 64 * 4));
+  HY3D_CUDA(ctx, kv.ktile.reserve((size_t)H * nkv * TILE_BYTES));
+  HY3D_CUDA(ctx, kv.vtile.reserve((size_t)H * nkv * TILE_BYTES));
+  HY3D_CUDA(ctx, ctx->ws[0].reserve(Mp * 3 * (size_t)(LW > W ? LW : W) * 2));    // T16 split of the latents / projected latents
+  HY3D_CUDA(ctx, ctx->ws[1].reserve(Mp * 3 * (size_t)W * 2 + Mp * S * 2 * 4));    // second T16 split + row statistics
+  uint8_t* tl = ctx->ws[0].as<uint8_t>();
+  uint8_t* tp = ctx->ws[1].as<uint8_t>();
+  float* st = reinterpret_cast<float*>(tp + Mp * 3 * (size_t)W * 2);
+  const uint8_t* a_kv = tl;
+  {
+    long long total = (long long)Mp * (LW / 8);
+    HY3D_PROF(ctx, FAM_KV);
+    k_rows_to_t16_split<<<(unsigned)ceil_div64(total, 256), 256, 0, ctx->stream>>>(d_latents, M, LW, tl);
+    HY3D_LAUNCH_CHECK(ctx);
+  }
+  if (w.has_latents_proj) {                                   // L = latents Wlp^T + blp; statistics for the folded ln_2 from the epilogue
+    GemmTC g{};
+    g.Mb = Mb; g.A = tl; g.B = reinterpret_cast<const uint8_t*>(w.t_lp3); g.KB = 3 * LW / 64; g.N = W; g.Nb = W / BN; g.bias = w.lp_b;
+    g.Tcopy = tp; g.split_out = 1; g.st_out = st; g.st_k = 2;
+    if (int rc = launch_gemm<EPI_X0>(ctx, g, FAM_KV)) return rc;
+    a_kv = tp;
+  } else {
+    long long warps = (long long)Mp * S;
+    HY3D_PROF(ctx, FAM_KV);
+    k_row_slot_stats<<<(unsigned)ceil_div64(warps * 32, 256), 256, 0, ctx->stream>>>(d_latents, M, W, st);
+    HY3D_LAUNCH_CHECK(ctx);
+  }
+  GemmTC g{};
+  g.Mb = Mb; g.A = a_kv; g.B = reinterpret_cast<const uint8_t*>(w.t_ckv3); g.KB = 3 * W / 64; g.N = 2 * W; g.Nb = 2 * W / BN; g.bias = w.bb_kv;
+  g.st_in = st; g.st_slots = S; g.st_np = 128; g.cs = w.cs_kv; g.ln_eps = 1e-6f;
+  g.Kout = kv.ktile.as<uint8_t>(); g.Vout = kv.vtile.as<uint8_t>(); g.nkv = nkv; g.Wq = W; g.part0 = 1;
+  g.kn_w = w.kn_w; g.kn_b = w.kn_b; g.qk_norm = w.qk_norm ? 1 : 0; g.qscale = 1.f;
+  g.K32 = kv.k32.as<float>(); g.V32T = kv.v32.as<float>(); g.Mtok = M;
+  if (int rc = launch_gemm<EPI_QKV>(ctx, g, FAM_KV)) return rc;
+  kv.M = M; kv.Mpad = (int)Mp; kv.ready = true;
   return 0;
 }
 
@@ -989,11 +925,6 @@ static int decode_tc_impl(hy3d_ctx* ctx, const QuerySource& src_in, long long n,
   float* st1 = ctx->ws[9].as<float>();
   float* st3 = st1 + (size_t)chmax * S * 2;
   float* stp = st3 + (size_t)chmax * S * 2;
-  HY3D_CUDA(ctx, cudaFuncSetAttribute(k_attn_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
-  HY3D_CUDA(ctx, cudaFuncSetAttribute(k_attn_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
-  HY3D_CUDA(ctx, cudaFuncSetAttribute(k_attn_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
-  HY3D_CUDA(ctx, cudaFuncSetAttribute(k_attn_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
-  HY3D_CUDA(ctx, cudaFuncSetAttribute(k_attn_tc<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
   const float pi_mul = w.include_pi ? 3.14159265358979323846f : 1.f;
   for (long long p0 = 0; p0 < n; p0 += CH) {
     const long long P = (n - p0 < CH) ? (n - p0) : CH;
@@ -1022,25 +953,14 @@ static int decode_tc_impl(hy3d_ctx* ctx, const QuerySource& src_in, long long n,
     if (int rc = hy3d_debug_keep(ctx, 2, ta, (size_t)Pp * W * 2, 2, Pp, W)) return rc;
     {
       AttnTC a{};
-      a.Q = ta; a.O = tq; a.Pb = Pb; a.H = H; a.stagger_ns = 0;
+      a.Q = ta; a.O = tq; a.Pb = Pb; a.H = H;
       if (d_tile_group) {
         a.K = ctx->kvsel.ktile.as<uint8_t>(); a.V = ctx->kvsel.vtile.as<uint8_t>(); a.nkv = ctx->kvsel.nkv;
         a.tile_group = d_tile_group + p0 / 128; a.group_ntok = ctx->kvsel.ntok.as<int>();
       } else {
         a.K = ctx->kv.ktile.as<uint8_t>(); a.V = ctx->kv.vtile.as<uint8_t>(); a.nkv = ctx->kv.Mpad / 128; a.ntok = ctx->kv.M;
       }
-      int items = Pb * (H / 2);
-      int grid = items < ctx->num_sms ? items : ctx->num_sms;
-      HY3D_PROF(ctx, FAM_ATTN);
-      switch (ctx->attn_poly) {
-        case 0: k_attn_tc<0><<<grid, ATT_THREADS, ATT_SMEM, ctx->stream>>>(a); break;
-        case 2: k_attn_tc<2><<<grid, ATT_THREADS, ATT_SMEM, ctx->stream>>>(a); break;
-        case 3: k_attn_tc<3><<<grid, ATT_THREADS, ATT_SMEM, ctx->stream>>>(a); break;
-        case 6: k_attn_tc<6><<<grid, ATT_THREADS, ATT_SMEM, ctx->stream>>>(a); break;
-        case 4: k_attn_tc<4><<<grid, ATT_THREADS, ATT_SMEM, ctx->stream>>>(a); break;
-        default: k_attn_tc<0><<<grid, ATT_THREADS, ATT_SMEM, ctx->stream>>>(a); break;
-      }
-      HY3D_LAUNCH_CHECK(ctx);
+      if (int rc = launch_attn(ctx, a, w.attn_fast, FAM_ATTN)) return rc;
     }
     if (int rc = hy3d_debug_keep(ctx, 3, tq, (size_t)Pp * W * 2, 2, Pp, W)) return rc;
     // x1 = x0 + c_proj(attn): fp32 residual in place + raw fp16 copy + statistics for the folded ln_3
@@ -1124,21 +1044,6 @@ int hy3d_tc_sample_q(hy3d_ctx* ctx, const QuerySource& src_in, long long n, floa
 // ------------------------------------------------------------------------------------------
 namespace {
 
-// fp32 rows [M, K] -> T16 split [hi | lo | hi]
-__global__ void k_rows_to_t16_split(const float* __restrict__ src, int M, int K, uint8_t* __restrict__ T) {
-  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // one 8-element chunk per thread
-  const int c8n = K / 8;
-  const long long rows_p = (long long)((M + 127) / 128) * 128;
-  if (t >= rows_p * c8n) return;
-  const int c8 = (int)(t % c8n); const long long row = t / c8n;
-  const int KBn = K / 64;
-  float v[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = row < M ? src[row * K + c8 * 8 + i] : 0.f;
-  uint8_t* t0 = T + ((size_t)(row / 128) * 3 * KBn + (c8 >> 3)) * TILE_BYTES;
-  store_t16_split(t0, t0 + (size_t)KBn * TILE_BYTES, t0 + (size_t)2 * KBn * TILE_BYTES, (int)(row % 128), c8 & 7, v);
-}
-
 __global__ void k_r32_to_rows(const float* __restrict__ R, long long rows, int W, float* __restrict__ out) {
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= rows * (W / 4)) return;
@@ -1184,7 +1089,7 @@ extern "C" int hy3d_set_transformer_weights(hy3d_ctx* ctx, const hy3d_transforme
   t.t_qkv.assign(L, nullptr); t.t_proj.assign(L, nullptr); t.t_fc.assign(L, nullptr); t.t_proj2.assign(L, nullptr);
   t.cs_qkv.assign(L, nullptr); t.bb_qkv.assign(L, nullptr); t.b_proj.assign(L, nullptr); t.cs_fc.assign(L, nullptr);
   t.bb_fc.assign(L, nullptr); t.b_proj2.assign(L, nullptr); t.qn_w.assign(L, nullptr); t.qn_b.assign(L, nullptr);
-  t.kn_w.assign(L, nullptr); t.kn_b.assign(L, nullptr);
+  t.kn_w.assign(L, nullptr); t.kn_b.assign(L, nullptr); t.attn_fast.assign(L, 0);
   for (size_t l = 0; l < L; ++l) {
     const hy3d_transformer_layer& y = d->layer[l];
     if (!y.ln1_w || !y.ln1_b || !y.c_qkv_w || !y.c_proj_w || !y.c_proj_b || !y.ln2_w || !y.ln2_b || !y.c_fc_w || !y.c_fc_b ||
@@ -1220,6 +1125,11 @@ extern "C" int hy3d_set_transformer_weights(hy3d_ctx* ctx, const hy3d_transforme
     }
     t.cs_qkv[l] = cs_qkv; t.bb_qkv[l] = bb_qkv; t.b_proj[l] = b_proj; t.cs_fc[l] = cs_fc; t.bb_fc[l] = bb_fc; t.b_proj2[l] = b_p2;
     t.qn_w[l] = nrm; t.qn_b[l] = nrm + 64; t.kn_w[l] = nrm + 128; t.kn_b[l] = nrm + 192;
+    if (d->qk_norm) {
+      float bound = INFINITY;
+      if (int rc = attn_score_bound(ctx, y.q_norm_w, y.q_norm_b, y.k_norm_w, y.k_norm_b, &bound)) return rc;
+      t.attn_fast[l] = bound <= ATT_FAST_BOUND ? 1 : 0;
+    }
   }
   HY3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // the fold scratch (ws[10]) is reused by other calls
   t.set = true;
@@ -1246,7 +1156,6 @@ extern "C" int hy3d_transformer_forward(hy3d_ctx* ctx, const float* d_z, int32_t
   float* x = t.x.as<float>();
   uint8_t *ta = t.ta.as<uint8_t>(), *tq = t.tq.as<uint8_t>(), *to = t.to.as<uint8_t>(), *th = t.th.as<uint8_t>();
   float* stA = t.st.as<float>(); float* stB = stA + Mp * S * 2;
-  HY3D_CUDA(ctx, cudaFuncSetAttribute(k_attn_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
   {
     long long total = (long long)M * (E / 8);
     HY3D_PROF(ctx, FAM_KV);
@@ -1268,11 +1177,7 @@ extern "C" int hy3d_transformer_forward(hy3d_ctx* ctx, const float* d_z, int32_t
     {
       AttnTC a{};
       a.Q = tq; a.O = to; a.Pb = Mb; a.H = H; a.K = t.kt.as<uint8_t>(); a.V = t.vt.as<uint8_t>(); a.nkv = Mb; a.ntok = M; a.split_out = 1;
-      int items = Mb * (H / 2);
-      int grid = items < ctx->num_sms ? items : ctx->num_sms;
-      HY3D_PROF(ctx, FAM_KV);
-      k_attn_tc<0><<<grid, ATT_THREADS, ATT_SMEM, ctx->stream>>>(a);
-      HY3D_LAUNCH_CHECK(ctx);
+      if (int rc = launch_attn(ctx, a, t.attn_fast[l] != 0, FAM_KV)) return rc;
     }
     g = GemmTC{}; g.Mb = Mb;                                   // x += c_proj(attn)
     g.A = to; g.B = t.t_proj[l]; g.KB = 3 * W / 64; g.N = W; g.Nb = W / BN; g.bias = t.b_proj[l];
@@ -1293,6 +1198,16 @@ extern "C" int hy3d_transformer_forward(hy3d_ctx* ctx, const float* d_z, int32_t
     k_r32_to_rows<<<(unsigned)ceil_div64(total, 256), 256, 0, ctx->stream>>>(x, M, W, d_out);
     HY3D_LAUNCH_CHECK(ctx);
   }
+  return HY3D_OK;
+}
+
+extern "C" int hy3d_debug_timers(hy3d_ctx* ctx, uint64_t h_out[32]) {
+  if (!ctx || !h_out) return HY3D_ERR_ARG;
+  HY3D_CUDA(ctx, cudaSetDevice(ctx->device));
+  HY3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  HY3D_CUDA(ctx, cudaMemcpyFromSymbol(h_out, hy3d_tm, sizeof(unsigned long long) * 32));
+  unsigned long long zero[32] = {};
+  HY3D_CUDA(ctx, cudaMemcpyToSymbol(hy3d_tm, zero, sizeof(zero)));
   return HY3D_OK;
 }
 

@@ -44,9 +44,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 #if HY3D_TC_WATCHDOG
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    ++spins;
-    const uint32_t limit = (*(volatile int*)&hy3d_wd[0]) ? (1u << 8) : (1u << 24);
-    if (spins > limit) {
+    if ((++spins & 0xffu) != 0) continue;          // the global flag is polled once per 256 failed tries: keep the wake-up path short
+    const uint32_t limit = (*(volatile int*)&hy3d_wd[0]) ? (1u << 8) : (1u << 22);
+    if (spins >= limit) {
       if (atomicExch(&hy3d_wd[0], 1) == 0) {
         hy3d_wd[1] = (int)blockIdx.x; hy3d_wd[2] = (int)threadIdx.x; hy3d_wd[3] = (int)bar; hy3d_wd[4] = (int)parity;
       }
@@ -56,6 +56,43 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 #else
   while (!mbar_try_wait(bar, parity)) {}
 #endif
+}
+
+// One lane of a fully converged warp.  The single-thread roles (TMA producer, MMA issuer) run their loops with
+// the whole warp converged and predicate only the issuing instructions on this: ptxas then keeps descriptors and
+// addresses in uniform registers.  Under a divergent `if (lane == 0)` every tcgen05.mma / cp.async.bulk instead
+// gets an ELECT + 5x R2UR + branch "waterfall" (~100 clk per MMA — more than a 128x128x16 MMA takes to execute).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
+// non-suspending variant: mbarrier.test_wait never parks the thread, so the waiter reacts within a few cycles of the
+// phase flip (try_wait may park it for a system-dependent time slice)
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_test_wait(bar, parity)) {
+    if ((++spins & 0xfffu) != 0) continue;
+    const uint32_t limit = (*(volatile int*)&hy3d_wd[0]) ? (1u << 12) : (1u << 26);
+    if (spins >= limit) {
+      if (atomicExch(&hy3d_wd[0], 1) == 0) {
+        hy3d_wd[1] = (int)blockIdx.x; hy3d_wd[2] = (int)threadIdx.x; hy3d_wd[3] = (int)bar; hy3d_wd[4] = (int)parity;
+      }
+      return;
+    }
+  }
 }
 
 // ---- async proxy ---------------------------------------------------------------------------
@@ -88,6 +125,15 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t adesc, uint
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]: A = 128 lanes (rows) x K 16-bit elements packed two per 32-bit column
+__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 // arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed

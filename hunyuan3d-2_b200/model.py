@@ -78,7 +78,7 @@ class B200ShapeVAE:
         if impl == "tc":
             from ._lib import get_context
             ctx = get_context(self.device)
-            ctx.set_transformer(self.sd, self.cfg, key=id(self.sd))
+            ctx.set_transformer(self.sd, self.cfg, key=id(self.sd), owner=self)
             z = latents.to(self.device)
             return torch.stack([ctx.transformer_forward(z[b]) for b in range(z.shape[0])], 0)
         return self._forward_torch(latents, dtype)

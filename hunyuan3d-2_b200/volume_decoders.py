@@ -85,7 +85,7 @@ def bind(latents: torch.Tensor, geo_decoder) -> GeoContext:
         raise RuntimeError("latents must live on a CUDA device (hy3dgeo has no CPU path)")
     ctx = get_context(latents.device)
     sd, cfg, key = _decoder_identity(geo_decoder)
-    ctx.set_decoder(sd, cfg, key)
+    ctx.set_decoder(sd, cfg, key, owner=geo_decoder)
     return ctx
 
 

@@ -199,6 +199,17 @@ int hy3d_debug_watchdog(hy3d_ctx* ctx, int32_t h_out[8]);
  * Stage ids: 0 x0, 1 ln_1(x0), 2 q after q_norm (the tcgen05 path stores q*scale*log2e),
  * 3 attention output, 4 x1, 5 ln_3(x1), 6 MLP hidden, 7 x2.  Costs one device copy per stage. */
 int hy3d_debug_retain(hy3d_ctx* ctx, int enable);
+/* Kernel-tuning experiments (tools/gpu_chain_bench.py): `bits` disables parts of the tcgen05 kernels
+ * (1 GEMM epilogue, 2 GEMM MMAs, 4 GEMM epilogue stores) so that their cost can be measured by difference — results
+ * are garbage while those are set; 0x20 forces the online-softmax attention kernel, 0x40 runs the instrumented
+ * bounded-score attention kernel (hy3d_debug_timers), 0x10000 the CUDA-core K/V projection (results stay valid);
+ * `attn_poly` = how many of every 8 attention exponentials run on the FMA pipe (0, 2, 3, 4, 6).
+ * Defaults (0, 0) are the product configuration. */
+int hy3d_debug_experiment(hy3d_ctx* ctx, int bits, int attn_poly);
+/* Phase clocks accumulated by the instrumented attention kernel (experiment bit 0x40), returned and cleared:
+ * per head stream a (0, 1) h_out[8a + i] = SM cycles one softmax thread of CTA 0 spent in phase i
+ * (0 wait S, 1 load S, 2 exponentials, 3 wait PV, 4 store P, 5 finalize), h_out[8a + 7] = KV tiles. */
+int hy3d_debug_timers(hy3d_ctx* ctx, uint64_t h_out[32]);
 /* Row-major fp32 [rows, *h_width] copy of a retained stage, whatever its internal layout. */
 int hy3d_debug_fetch(hy3d_ctx* ctx, int stage, float* d_out, int64_t rows, int32_t* h_width);
 
