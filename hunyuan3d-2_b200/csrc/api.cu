@@ -124,7 +124,7 @@ void hy3d_destroy(hy3d_ctx* ctx) {
   { TransformerState& t = ctx->tf; for (DevBuf* b : {&t.tc, &t.f32, &t.x, &t.ta, &t.tq, &t.to, &t.th, &t.kt, &t.vt, &t.st, &t.tz}) b->release(); }
   ctx->w.fold.release();
   { KVSelState& k = ctx->kvsel; k.ktile.release(); k.vtile.release(); k.ntok.release(); k.sel.release(); k.qs.release(); k.qbar.release(); k.mask.release(); }
-  ctx->scratch.release(); ctx->scratch2.release();
+  ctx->scratch.release(); ctx->scratch2.release(); ctx->ln_mr.release();
   for (auto& b : ctx->dbg) b.release();
   for (auto& r : ctx->prof.recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   for (auto e : ctx->prof.pool) cudaEventDestroy(e);

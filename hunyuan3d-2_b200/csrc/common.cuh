@@ -119,6 +119,7 @@ struct hy3d_ctx {
   McState mc;
   DevBuf ws[12];                      // decoder workspaces
   DevBuf scratch, scratch2;           // octree / misc
+  DevBuf ln_mr;                       // per-row (mean, rstd) of the LayerNorm folded into the running GEMM
   void* pinned = nullptr;             // small pinned host buffer for read-backs
   Prof prof;
   // diagnostics: per-stage activations of the last decoded chunk (hy3d_debug_retain / hy3d_debug_fetch)

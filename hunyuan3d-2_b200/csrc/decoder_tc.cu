@@ -37,7 +37,9 @@ constexpr int TILE_BYTES = 16384;          // 128 x 64 fp16
 constexpr int BN = 256;                    // GEMM N tile
 constexpr int BTILE_BYTES = BN * 128;      // 256 x 64 fp16
 constexpr int GEMM_STAGES = 4;
-constexpr int GEMM_THREADS = 384;          // warp0 producer, warp1 mma, warp2 tmem, warp3 idle, warps 4..11 epilogue
+constexpr int GEMM_THREADS = 640;          // warp0 producer, warp1 mma, warp2 tmem, warp3 idle, warps 4..19 epilogue
+constexpr int ST_PER_TILE = 4;             // row-statistic slots per 256-column tile (one per epilogue warp column quarter)
+constexpr int ST_COLS = BN / ST_PER_TILE;  // columns per slot (64)
 constexpr float LOG2E = 1.4426950408889634f;
 
 enum { EPI_X0 = 0, EPI_Q = 1, EPI_RES = 2, EPI_GELU = 3, EPI_QF32 = 4, EPI_QKV = 5 };
@@ -56,6 +58,7 @@ struct GemmTC {
   // so  LN(x) W^T = rstd * (x W'^T - mean * cs) + (beta W^T + bias);  row statistics come as S partial
   // (mean, M2) slots written by the producer's epilogue and are merged here (Chan et al.), deterministically.
   const float* st_in; int st_slots; int st_np; const float* cs; float ln_eps;
+  const float2* ln_mr;   // per row (mean, rstd) merged from st_in by k_finish_stats (set by launch_gemm)
   // statistics of the rows this GEMM produces (EPI_X0 / EPI_RES): slot nb*2+half <- (mean, M2[, dot with dotw])
   float* st_out; int st_k; const float* dotw;
   uint8_t* Tcopy;        // fp16 T16 copy of the fp32 rows written to Rout (operand of the next GEMM)
@@ -79,15 +82,25 @@ __device__ __forceinline__ void merge_row_stats(const float* __restrict__ st, in
 }
 
 // exact-erf GELU (reference attention_blocks.py:177) without erff's two divergent branches:
-// 1 - erf(t) = 2^(-t g(t)), g a degree-5 minimax fit on [0,4] (tools fit: |erf err| < 3e-7,
-// |gelu err| < 7e-7 in fp32 — far below the fp16 rounding of the stored activation).
+//   gelu(x) = max(x, 0) - |x| * erfc(|x| / sqrt2) / 2,   erfc(t) = 2^(-t g(t)),  g a minimax fit on [0, 4]
+// (beyond t = 4 the correction is < 1e-8 |x| and the clamp keeps it there).  The 1/2 rides in the exponent.
+// kDeg = 5: |gelu err| < 1e-7 (fp32-grade, latent transformer);  kDeg = 3: < 9e-6, far below the fp16
+// rounding of the stored activation (decoder MLP) for two FFMA less per element.
+template <int kDeg>
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float t = fminf(fabsf(x) * 0.70710678118654752440f, 4.0f);
-  float g = -1.588800078e-04f;
-  g = fmaf(g, t, 3.746585688e-03f); g = fmaf(g, t, -3.103881516e-02f); g = fmaf(g, t, 1.498060673e-01f);
-  g = fmaf(g, t, 9.181324244e-01f); g = fmaf(g, t, 1.627928257e+00f);
-  const float e = ex2(-t * g);                   // erfc(|x|/sqrt2)
-  return 0.5f * x * (x > 0.f ? 2.f - e : e);
+  const float ax = fabsf(x);
+  const float t = fminf(ax * 0.70710678118654752440f, 4.0f);
+  float g;
+  if constexpr (kDeg == 5) {
+    g = -2.39272936e-04f;
+    g = fmaf(g, t, 4.18474770e-03f); g = fmaf(g, t, -3.19086965e-02f); g = fmaf(g, t, 1.50579343e-01f);
+    g = fmaf(g, t, 9.17831750e-01f); g = fmaf(g, t, 1.62796776e+00f);
+  } else {
+    g = -1.664811e-02f;
+    g = fmaf(g, t, 1.2936552e-01f); g = fmaf(g, t, 9.2985345e-01f); g = fmaf(g, t, 1.62573555e+00f);
+  }
+  const float e = ex2(fmaf(-t, g, -1.0f));        // erfc(|x| / sqrt2) / 2
+  return fmaxf(x, 0.f) - ax * e;
 }
 
 __device__ __forceinline__ void store_t16_chunk(uint8_t* tile, int r, int c16, const float* v) {
@@ -110,8 +123,13 @@ __device__ __forceinline__ void store_t16_split(uint8_t* t0, uint8_t* t1, uint8_
 // ------------------------------------------------------------------------------------------
 // Persistent warp-specialised GEMM:  C[P, N] = A[P, K] * W[N, K]^T with a fused epilogue.
 // ------------------------------------------------------------------------------------------
+// Clusters of two CTAs work on two vertically adjacent 128 x 256 tiles (same weight tile): each CTA fetches its own A
+// tile and ONE HALF of the B tile, multicast into both CTAs' shared memory, so a tile costs 32 KB of L2 -> SM traffic
+// per k-block instead of 48 KB.  (Measured: with every CTA fetching all 48 KB the loads alone run at 85 % of the
+// MMA-only rate, and the K = 1024 GEMMs sit at the L2 -> SM bandwidth, not at the tensor pipe.)  A stage may be
+// refilled only when BOTH CTAs' MMAs have consumed it: the MMA warp's commit is multicast to both EMPTY barriers.
 template <int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(GemmTC g) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(GemmTC g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;                                      // [STAGES][16 KB]
@@ -126,30 +144,36 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(GemmTC g) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * GEMM_STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long clk0 = (g.dbg & 8) ? clock64() : 0;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < GEMM_STAGES; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(TFULL(a), 1); mbar_init(TEMPTY(a), 8); }
+    for (int s = 0; s < GEMM_STAGES; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 2); }
+    for (int a = 0; a < 2; ++a) { mbar_init(TFULL(a), 1); mbar_init(TEMPTY(a), 16); }
     fence_barrier_init();
   }
   if (warp == 2) { tmem_alloc(smem_u32(tmem_slot), 512); tmem_relinquish(); }
   fence_before_sync();
-  __syncthreads();
+  cluster_sync();                      // the peer's barriers must exist before anything is multicast to them
   fence_after_sync();
   const uint32_t tmem = *tmem_slot;
-  const int ntiles = g.Mb * g.Nb;
+  // work item p of cluster c: tile pair (m-blocks 2 (p / Nb) + {0, 1}, n-block p % Nb); this CTA takes m-block + rank
+  const int rank = (int)cluster_ctarank();
+  const int npairs = ((g.Mb + 1) / 2) * g.Nb;
+  const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
 
   if (warp == 0) {
     int s = 0; uint32_t ph = 0;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-      const int mb = t / g.Nb, nb = t % g.Nb;
+    for (int p = cid; p < npairs; p += ncl) {
+      int mb = 2 * (p / g.Nb) + rank; const int nb = p % g.Nb;
+      if (mb >= g.Mb) mb = g.Mb - 1;   // odd tile count: the idle half still feeds its share of B (its results are dropped)
       const uint8_t* a = g.A + (size_t)mb * g.KB * TILE_BYTES;
-      const uint8_t* b = g.B + (size_t)nb * g.KB * BTILE_BYTES;
+      const uint8_t* b = g.B + (size_t)nb * g.KB * BTILE_BYTES + rank * (BTILE_BYTES / 2);
       for (int kb = 0; kb < g.KB; ++kb) {
         mbar_wait(EMPTY(s), ph ^ 1);
         if (elect_one()) {
           mbar_arrive_expect_tx(FULL(s), TILE_BYTES + BTILE_BYTES);
           bulk_g2s(smem_u32(sA + s * TILE_BYTES), a + (size_t)kb * TILE_BYTES, TILE_BYTES, FULL(s));
-          bulk_g2s(smem_u32(sB + s * BTILE_BYTES), b + (size_t)kb * BTILE_BYTES, BTILE_BYTES, FULL(s));
+          bulk_g2s_multicast(smem_u32(sB + s * BTILE_BYTES + rank * (BTILE_BYTES / 2)), b + (size_t)kb * BTILE_BYTES, BTILE_BYTES / 2,
+                             FULL(s), (uint16_t)3);
         }
         __syncwarp();
         if (++s == GEMM_STAGES) { s = 0; ph ^= 1; }
@@ -159,7 +183,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(GemmTC g) {
     const uint32_t idesc = make_idesc_f16(TILE_M, BN);
     int s = 0; uint32_t ph = 0;
     int it = 0;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+    for (int p = cid; p < npairs; p += ncl, ++it) {
       const int acc = it & 1;
       const uint32_t aph = (it >> 1) & 1;
       mbar_wait(TEMPTY(acc), aph ^ 1);
@@ -174,7 +198,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(GemmTC g) {
           if (!(g.dbg & 2))
 #pragma unroll
             for (int k = 0; k < 4; ++k) mma_f16_ss(d, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
-          mma_commit(EMPTY(s));
+          mma_commit_multicast(EMPTY(s), (uint16_t)3);
           if (kb == g.KB - 1) mma_commit(TFULL(acc));
         }
         __syncwarp();
@@ -182,167 +206,152 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(GemmTC g) {
       }
     }
   } else if (warp >= 4) {
-    const int e = warp - 4;
+    // ---------------- epilogue: 16 warps = 4 TMEM lane quadrants x 4 column quarters of 64 ----------------
+    // (four warps per scheduler: the TMEM-load -> constants -> math -> store chain of one warp hides behind the others)
     const int q = warp & 3;                 // TMEM lane quadrant this warp may access
-    const int half = e >> 2;                // column half of the 256-wide tile
+    const int cq = (warp - 4) >> 2;         // 64-column quarter of the 256-wide tile
     const int r = q * 32 + lane;            // row inside the tile
     int it = 0;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-      const int mb = t / g.Nb, nb = t % g.Nb;
+    for (int p = cid; p < npairs; p += ncl, ++it) {
+      const int mb = 2 * (p / g.Nb) + rank, nb = p % g.Nb;
       const int acc = it & 1;
       const uint32_t aph = (it >> 1) & 1;
       mbar_wait(TFULL(acc), aph);
       fence_after_sync();
-      if (g.dbg & 1) { fence_before_sync(); __syncwarp(); if (lane == 0) mbar_arrive(TEMPTY(acc)); continue; }
-      const uint32_t trow = tmem + acc * BN + ((uint32_t)(q * 32) << 16);
-      const int col0 = nb * BN + half * (BN / 2);          // first global column of this warp's half
+      if ((g.dbg & 1) || mb >= g.Mb) { fence_before_sync(); __syncwarp(); if (lane == 0) mbar_arrive(TEMPTY(acc)); continue; }
+      const uint32_t tcol = tmem + acc * BN + cq * 64 + ((uint32_t)(q * 32) << 16);
+      const int c0 = nb * BN + cq * 64;     // first global column of this warp's quarter
       float ln_mean = 0.f, ln_rstd = 1.f;
-      if (g.st_in) merge_row_stats(g.st_in + ((size_t)mb * TILE_M + r) * g.st_slots * 2, g.st_slots, 2, g.st_np,
-                                   g.ln_eps, ln_mean, ln_rstd);
+      if (g.st_in) { const float2 mr = __ldg(g.ln_mr + (size_t)mb * TILE_M + r); ln_mean = mr.x; ln_rstd = mr.y; }
+      const float nm = -ln_rstd * ln_mean;
+      // 32 accumulator columns [c0 + 32 ch, +32) -> x: + bias, or the folded LayerNorm  rstd * a + (bb - rstd * mean * cs)
+      auto load32 = [&](int ch, float* x, bool fold) {
+        uint32_t v[32];
+        HY3D_TMEM_LD32(tcol + ch * 32, v);
+        tmem_wait_ld();
+        const float4* b4 = reinterpret_cast<const float4*>(g.bias + c0 + ch * 32);
+        const float4* c4 = reinterpret_cast<const float4*>(g.cs + c0 + ch * 32);
+#pragma unroll
+        for (int i4 = 0; i4 < 8; ++i4) {
+          float4 bv = g.bias ? __ldg(b4 + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float a0 = __uint_as_float(v[4 * i4]), a1 = __uint_as_float(v[4 * i4 + 1]);
+          const float a2 = __uint_as_float(v[4 * i4 + 2]), a3 = __uint_as_float(v[4 * i4 + 3]);
+          if (fold) {
+            const float4 cv = __ldg(c4 + i4);
+            x[4 * i4] = fmaf(ln_rstd, a0, fmaf(nm, cv.x, bv.x)); x[4 * i4 + 1] = fmaf(ln_rstd, a1, fmaf(nm, cv.y, bv.y));
+            x[4 * i4 + 2] = fmaf(ln_rstd, a2, fmaf(nm, cv.z, bv.z)); x[4 * i4 + 3] = fmaf(ln_rstd, a3, fmaf(nm, cv.w, bv.w));
+          } else {
+            x[4 * i4] = a0 + bv.x; x[4 * i4 + 1] = a1 + bv.y; x[4 * i4 + 2] = a2 + bv.z; x[4 * i4 + 3] = a3 + bv.w;
+          }
+        }
+      };
       if constexpr (EPI == EPI_Q || EPI == EPI_QF32 || EPI == EPI_QKV) {
+        // this warp's 64 columns are exactly one head: per-head LayerNorm (q_norm / k_norm) in two passes over TMEM
+        const bool fold = g.st_in != nullptr;
+        int part = 0, cpart = 0;                            // 0 q, 1 k, 2 v (EPI_QKV); q otherwise
+        if constexpr (EPI == EPI_QKV) { cpart = c0 / g.Wq; part = cpart + g.part0; }
+        const float* nw = part == 1 ? g.kn_w : g.qn_w;
+        const float* nbp = part == 1 ? g.kn_b : g.qn_b;
+        const float oscale = part == 0 ? g.qscale : 1.f;
+        const bool norm = g.qk_norm && part < 2;
+        float mean = 0.f, rs = oscale;
+        if (norm) {
+          float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
-        for (int hh = 0; hh < 2; ++hh) {                    // two 64-column heads per half
-          uint32_t v[64];
-          HY3D_TMEM_LD32(trow + half * (BN / 2) + hh * 64, v);
-          HY3D_TMEM_LD32(trow + half * (BN / 2) + hh * 64 + 32, (v + 32));
-          tmem_wait_ld();
-          const int c = col0 + hh * 64;
-          float x[64];
+          for (int ch = 0; ch < 2; ++ch) {
+            float x[32];
+            load32(ch, x, fold);
 #pragma unroll
-          {
-            const float4* b4 = reinterpret_cast<const float4*>(g.bias + c);
-            const float4* c4 = reinterpret_cast<const float4*>(g.cs + c);
-            const float nm = -ln_rstd * ln_mean;
-#pragma unroll
-            for (int i4 = 0; i4 < 16; ++i4) {
-              const float4 bv = g.bias ? __ldg(b4 + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
-              float a0 = __uint_as_float(v[4 * i4]), a1 = __uint_as_float(v[4 * i4 + 1]);
-              float a2 = __uint_as_float(v[4 * i4 + 2]), a3 = __uint_as_float(v[4 * i4 + 3]);
-              if (g.st_in) {
-                const float4 cv = __ldg(c4 + i4);
-                a0 = fmaf(ln_rstd, a0, nm * cv.x); a1 = fmaf(ln_rstd, a1, nm * cv.y);
-                a2 = fmaf(ln_rstd, a2, nm * cv.z); a3 = fmaf(ln_rstd, a3, nm * cv.w);
-              }
-              x[4 * i4] = a0 + bv.x; x[4 * i4 + 1] = a1 + bv.y; x[4 * i4 + 2] = a2 + bv.z; x[4 * i4 + 3] = a3 + bv.w;
-            }
+            for (int i = 0; i < 32; ++i) { s1 += x[i]; s2 = fmaf(x[i], x[i], s2); }
           }
-          int part = 0, cpart = 0;                            // 0 q, 1 k, 2 v (EPI_QKV); q otherwise
-          if constexpr (EPI == EPI_QKV) { cpart = c / g.Wq; part = cpart + g.part0; }
-          const float* nw = part == 1 ? g.kn_w : g.qn_w;
-          const float* nb = part == 1 ? g.kn_b : g.qn_b;
-          const float oscale = part == 0 ? g.qscale : 1.f;
-          if (g.qk_norm && part < 2) {
-            float s = 0.f;
+          mean = s1 * (1.f / 64.f);
+          rs = rsqrtf(fmaxf(s2 * (1.f / 64.f) - mean * mean, 0.f) + 1e-6f) * oscale;
+        }
+        const int row = mb * TILE_M + r;
+        const bool pad = (EPI == EPI_QKV) && g.Mtok > 0 && row >= g.Mtok;      // padding tokens: exact zeros
+        const int h = (EPI == EPI_QKV) ? (c0 - cpart * g.Wq) >> 6 : c0 >> 6;
+#pragma unroll 1
+        for (int ch = 0; ch < 2; ++ch) {
+          float x[32];
+          load32(ch, x, fold);
+          if (norm) {
 #pragma unroll
-            for (int i = 0; i < 64; ++i) s += x[i];
-            const float mean = s * (1.f / 64.f);
-            float var = 0.f;
-#pragma unroll
-            for (int i = 0; i < 64; ++i) { float d = x[i] - mean; var += d * d; }
-            const float rstd = rsqrtf(var * (1.f / 64.f) + 1e-6f);
-#pragma unroll
-            for (int i4 = 0; i4 < 16; ++i4) {
-              const float4 gw = __ldg(reinterpret_cast<const float4*>(nw) + i4), gb = __ldg(reinterpret_cast<const float4*>(nb) + i4);
-              x[4 * i4] = ((x[4 * i4] - mean) * rstd * gw.x + gb.x) * oscale;
-              x[4 * i4 + 1] = ((x[4 * i4 + 1] - mean) * rstd * gw.y + gb.y) * oscale;
-              x[4 * i4 + 2] = ((x[4 * i4 + 2] - mean) * rstd * gw.z + gb.z) * oscale;
-              x[4 * i4 + 3] = ((x[4 * i4 + 3] - mean) * rstd * gw.w + gb.w) * oscale;
+            for (int i4 = 0; i4 < 8; ++i4) {                // (x - mean) * (rstd * scale * gamma) + scale * beta
+              const float4 gw = __ldg(reinterpret_cast<const float4*>(nw) + ch * 8 + i4);
+              const float4 gb = __ldg(reinterpret_cast<const float4*>(nbp) + ch * 8 + i4);
+              x[4 * i4] = fmaf(x[4 * i4] - mean, rs * gw.x, gb.x * oscale);
+              x[4 * i4 + 1] = fmaf(x[4 * i4 + 1] - mean, rs * gw.y, gb.y * oscale);
+              x[4 * i4 + 2] = fmaf(x[4 * i4 + 2] - mean, rs * gw.z, gb.z * oscale);
+              x[4 * i4 + 3] = fmaf(x[4 * i4 + 3] - mean, rs * gw.w, gb.w * oscale);
             }
           } else {
 #pragma unroll
-            for (int i = 0; i < 64; ++i) x[i] *= oscale;
+            for (int i = 0; i < 32; ++i) x[i] *= oscale;
           }
-          if constexpr (EPI == EPI_QF32) {
-            float4* o = reinterpret_cast<float4*>(g.Fout + ((size_t)mb * TILE_M + r) * g.N + c);
+          if (pad) {
 #pragma unroll
-            for (int i4 = 0; i4 < 16; ++i4) o[i4] = make_float4(x[4 * i4], x[4 * i4 + 1], x[4 * i4 + 2], x[4 * i4 + 3]);
-          } else if constexpr (EPI == EPI_QKV) {
-            const int h = (c - cpart * g.Wq) >> 6;
-            const int row = mb * TILE_M + r;
-            if (g.Mtok > 0 && row >= g.Mtok) {                // padding tokens: exact zeros
-#pragma unroll
-              for (int i = 0; i < 64; ++i) x[i] = 0.f;
-            }
-            if (part == 1 && g.K32 && row < g.Mtok) {
-              float4* o = reinterpret_cast<float4*>(g.K32 + ((size_t)h * g.Mtok + row) * 64);
-#pragma unroll
-              for (int i4 = 0; i4 < 16; ++i4) o[i4] = make_float4(x[4 * i4], x[4 * i4 + 1], x[4 * i4 + 2], x[4 * i4 + 3]);
-            }
-            if (part == 2 && g.V32T && row < g.Mtok) {
-              float* o = g.V32T + (size_t)h * 64 * g.Mtok + row;
-#pragma unroll
-              for (int d = 0; d < 64; ++d) o[(size_t)d * g.Mtok] = x[d];
-            }
-            if (part == 0) {                                  // q: T16 [Mb][H], k-block == head
-              uint8_t* tile = g.Tout + ((size_t)mb * (g.Wq / 64) + h) * TILE_BYTES;
-#pragma unroll
-              for (int c16 = 0; c16 < 8; ++c16) store_t16_chunk(tile, r, c16, x + 8 * c16);
-            } else if (part == 1) {                           // k: K tiles [H][nkv][128 tok x 64]
-              uint8_t* tile = g.Kout + ((size_t)h * g.nkv + mb) * TILE_BYTES;
-#pragma unroll
-              for (int c16 = 0; c16 < 8; ++c16) store_t16_chunk(tile, r, c16, x + 8 * c16);
-            } else {                                          // v: V^T tiles [H][nkv][2][64 d x 64 tok] — transposed 2-byte stores
-              uint8_t* tile = g.Vout + ((size_t)h * g.nkv + mb) * TILE_BYTES + (r >> 6) * (TILE_BYTES / 2) + (r & 7) * 2;
-              const int c16 = (r & 63) >> 3;
-#pragma unroll
-              for (int d = 0; d < 64; ++d) *reinterpret_cast<__half*>(tile + sw128_off(d, c16)) = __float2half_rn(x[d]);
-            }
-          } else if (!(g.dbg & 4)) {
-            uint8_t* tile = g.Tout + ((size_t)mb * (g.N / 64) + (c >> 6)) * TILE_BYTES;
-#pragma unroll
-            for (int c16 = 0; c16 < 8; ++c16) store_t16_chunk(tile, r, c16, x + 8 * c16);
-          } else {
+            for (int i = 0; i < 32; ++i) x[i] = 0.f;
+          }
+          if (g.dbg & 4) {
             float acc_ = 0.f;
 #pragma unroll
-            for (int i = 0; i < 64; ++i) acc_ += x[i];
+            for (int i = 0; i < 32; ++i) acc_ += x[i];
             if (acc_ == 123.456f) g.Tout[0] = 1;
+          } else if constexpr (EPI == EPI_QF32) {
+            float4* o = reinterpret_cast<float4*>(g.Fout + (size_t)row * g.N + c0 + ch * 32);
+#pragma unroll
+            for (int i4 = 0; i4 < 8; ++i4) o[i4] = make_float4(x[4 * i4], x[4 * i4 + 1], x[4 * i4 + 2], x[4 * i4 + 3]);
+          } else if (part == 2) {                           // v: V^T tiles [H][nkv][2][64 d x 64 tok] — transposed 2-byte stores
+            if (g.V32T && row < g.Mtok) {
+              float* o = g.V32T + ((size_t)h * 64 + ch * 32) * g.Mtok + row;
+#pragma unroll
+              for (int d = 0; d < 32; ++d) o[(size_t)d * g.Mtok] = x[d];
+            }
+            uint8_t* tile = g.Vout + ((size_t)h * g.nkv + mb) * TILE_BYTES + (r >> 6) * (TILE_BYTES / 2) + (r & 7) * 2;
+            const int c16 = (r & 63) >> 3;
+#pragma unroll
+            for (int d = 0; d < 32; ++d) *reinterpret_cast<__half*>(tile + sw128_off(ch * 32 + d, c16)) = __float2half_rn(x[d]);
+          } else {                                          // q (T16 [Mb][heads], k-block == head) or k (K tiles [H][nkv])
+            if (part == 1 && g.K32 && row < g.Mtok) {
+              float4* o = reinterpret_cast<float4*>(g.K32 + ((size_t)h * g.Mtok + row) * 64 + ch * 32);
+#pragma unroll
+              for (int i4 = 0; i4 < 8; ++i4) o[i4] = make_float4(x[4 * i4], x[4 * i4 + 1], x[4 * i4 + 2], x[4 * i4 + 3]);
+            }
+            uint8_t* tile = part == 1 ? g.Kout + ((size_t)h * g.nkv + mb) * TILE_BYTES
+                                      : g.Tout + ((size_t)mb * ((EPI == EPI_QKV ? g.Wq : g.N) / 64) + h) * TILE_BYTES;
+#pragma unroll
+            for (int c16 = 0; c16 < 4; ++c16) store_t16_chunk(tile, r, ch * 4 + c16, x + 8 * c16);
           }
         }
       } else {
-        float rn = 0.f, rmean = 0.f, rM2 = 0.f, rdot = 0.f;  // running statistics of this thread's 128 output columns
+        float rn = 0.f, rmean = 0.f, rM2 = 0.f, rdot = 0.f;  // running statistics of this thread's 64 output columns
 #pragma unroll 1
-        for (int ch = 0; ch < 4; ++ch) {                    // four 32-column chunks per half
-          uint32_t v[32];
-          HY3D_TMEM_LD32(trow + half * (BN / 2) + ch * 32, v);
-          tmem_wait_ld();
-          const int c = col0 + ch * 32;
+        for (int ch = 0; ch < 2; ++ch) {
+          const int c = c0 + ch * 32;
           float x[32];
-          {  // per-column constants: warp-uniform 16-byte loads (bias / folded-LN column sums)
-            const float4* b4 = reinterpret_cast<const float4*>(g.bias + c);
-            const float4* c4 = reinterpret_cast<const float4*>(g.cs + c);
-            const bool fold = (EPI == EPI_GELU) && g.st_in != nullptr;
-            const float nm = -ln_rstd * ln_mean;
-#pragma unroll
-            for (int i4 = 0; i4 < 8; ++i4) {
-              const float4 bv = g.bias ? __ldg(b4 + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
-              float a0 = __uint_as_float(v[4 * i4]), a1 = __uint_as_float(v[4 * i4 + 1]);
-              float a2 = __uint_as_float(v[4 * i4 + 2]), a3 = __uint_as_float(v[4 * i4 + 3]);
-              if (fold) {      // rstd * (a - mean * cs) + bb
-                const float4 cv = __ldg(c4 + i4);
-                a0 = fmaf(ln_rstd, a0, nm * cv.x); a1 = fmaf(ln_rstd, a1, nm * cv.y);
-                a2 = fmaf(ln_rstd, a2, nm * cv.z); a3 = fmaf(ln_rstd, a3, nm * cv.w);
-              }
-              x[4 * i4] = a0 + bv.x; x[4 * i4 + 1] = a1 + bv.y; x[4 * i4 + 2] = a2 + bv.z; x[4 * i4 + 3] = a3 + bv.w;
-            }
-          }
+          load32(ch, x, (EPI == EPI_GELU) && g.st_in != nullptr);
           if constexpr (EPI == EPI_GELU) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) x[i] = gelu_erf(x[i]);
-            const int KBn = g.N / 64;
-            uint8_t* tile = g.Tout + ((size_t)mb * (g.split_out ? 3 : 1) * KBn + (c >> 6)) * TILE_BYTES;
-            const int cbase = (c & 63) >> 3;
             if (g.split_out) {
 #pragma unroll
-              for (int c16 = 0; c16 < 4; ++c16)
-                store_t16_split(tile, tile + (size_t)KBn * TILE_BYTES, tile + (size_t)2 * KBn * TILE_BYTES, r, cbase + c16, x + 8 * c16);
-            } else if (!(g.dbg & 4)) {
-#pragma unroll
-              for (int c16 = 0; c16 < 4; ++c16) store_t16_chunk(tile, r, cbase + c16, x + 8 * c16);
+              for (int i = 0; i < 32; ++i) x[i] = gelu_erf<5>(x[i]);
             } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) x[i] = gelu_erf<3>(x[i]);
+            }
+            const int KBn = g.N / 64;
+            uint8_t* tile = g.Tout + ((size_t)mb * (g.split_out ? 3 : 1) * KBn + (c >> 6)) * TILE_BYTES;
+            if (g.dbg & 4) {
               float acc_ = 0.f;
 #pragma unroll
               for (int i = 0; i < 32; ++i) acc_ += x[i];
               if (acc_ == 123.456f) g.Tout[0] = 1;
+            } else if (g.split_out) {
+#pragma unroll
+              for (int c16 = 0; c16 < 4; ++c16)
+                store_t16_split(tile, tile + (size_t)KBn * TILE_BYTES, tile + (size_t)2 * KBn * TILE_BYTES, r, ch * 4 + c16, x + 8 * c16);
+            } else {
+#pragma unroll
+              for (int c16 = 0; c16 < 4; ++c16) store_t16_chunk(tile, r, ch * 4 + c16, x + 8 * c16);
             }
           } else {
             // R32: [mb][c/4][row][4]
@@ -361,14 +370,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(GemmTC g) {
             if (g.Tcopy && !(g.dbg & 4)) {
               const int KBn = g.N / 64;
               uint8_t* tile = g.Tcopy + ((size_t)mb * (g.split_out ? 3 : 1) * KBn + (c >> 6)) * TILE_BYTES;
-              const int cbase = (c & 63) >> 3;
               if (g.split_out) {
 #pragma unroll
                 for (int c16 = 0; c16 < 4; ++c16)
-                  store_t16_split(tile, tile + (size_t)KBn * TILE_BYTES, tile + (size_t)2 * KBn * TILE_BYTES, r, cbase + c16, x + 8 * c16);
+                  store_t16_split(tile, tile + (size_t)KBn * TILE_BYTES, tile + (size_t)2 * KBn * TILE_BYTES, r, ch * 4 + c16, x + 8 * c16);
               } else {
 #pragma unroll
-                for (int c16 = 0; c16 < 4; ++c16) store_t16_chunk(tile, r, cbase + c16, x + 8 * c16);
+                for (int c16 = 0; c16 < 4; ++c16) store_t16_chunk(tile, r, ch * 4 + c16, x + 8 * c16);
               }
             }
             if (g.st_out) {
@@ -395,8 +403,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(GemmTC g) {
           }
         }
         if constexpr (EPI == EPI_X0 || EPI == EPI_RES) {
-          if (g.st_out) {
-            float* so = g.st_out + (((size_t)mb * TILE_M + r) * (2 * g.Nb) + nb * 2 + half) * g.st_k;
+          if (g.st_out) {                                    // slot nb * 4 + cq  <-  (mean, M2[, dot]) of 64 columns
+            float* so = g.st_out + (((size_t)mb * TILE_M + r) * (ST_PER_TILE * g.Nb) + nb * ST_PER_TILE + cq) * g.st_k;
             so[0] = rmean; so[1] = rM2;
             if (g.st_k == 3) so[2] = rdot;
           }
@@ -408,8 +416,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(GemmTC g) {
     }
   }
   fence_before_sync();
-  __syncthreads();
+  cluster_sync();                      // the peer may still be signalling this CTA's barriers
   if (warp == 2) tmem_dealloc(tmem, 512);
+  if ((g.dbg & 8) && threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(&hy3d_tm[24 + EPI], (unsigned long long)(clock64() - clk0));   // SM cycles of this launch
 }
 
 constexpr size_t GEMM_SMEM = 1024 + GEMM_STAGES * (TILE_BYTES + BTILE_BYTES) + 256;
@@ -666,13 +675,39 @@ __global__ void k_build_kv(const float* __restrict__ k32, const float* __restric
   }
 }
 
+// (mean, rstd) per row from the S partial (mean, M2) slots a producer epilogue wrote: once per row here, instead of
+// S strided loads per row in every consumer tile (which made the consumer epilogues LSU-bound)
+__global__ void k_finish_stats(const float* __restrict__ st, int S, int n_p, float eps, long long rows, float2* __restrict__ out) {
+  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= rows) return;
+  float mean, rstd;
+  merge_row_stats(st + row * S * 2, S, 2, n_p, eps, mean, rstd);
+  out[row] = make_float2(mean, rstd);
+}
+
 template <int EPI>
 int launch_gemm(hy3d_ctx* ctx, const GemmTC& g, int fam) {
   HY3D_CUDA(ctx, cudaFuncSetAttribute(k_gemm_tc<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
-  int tiles = g.Mb * g.Nb;
-  int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
+  static int max_clusters = 0;                                     // co-resident 2-CTA clusters (persistent grid)
+  if (max_clusters == 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ctx->num_sms / 2 * 2); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = GEMM_SMEM;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, k_gemm_tc<EPI>, &cfg) != cudaSuccess || n <= 0) { n = ctx->num_sms / 2; (void)cudaGetLastError(); }
+    max_clusters = n < ctx->num_sms / 2 ? n : ctx->num_sms / 2;
+    if (getenv("HY3D_VERBOSE")) fprintf(stderr, "[hy3dgeo] k_gemm_tc<%d>: %d co-resident 2-CTA clusters\n", EPI, max_clusters);
+  }
+  const int pairs = ((g.Mb + 1) / 2) * g.Nb;                       // one tile pair per cluster iteration
+  const int grid = 2 * (pairs < max_clusters ? pairs : max_clusters);
   HY3D_PROF(ctx, fam);
-  GemmTC gd = g; gd.dbg = ctx->xbits & 7;
+  GemmTC gd = g; gd.dbg = ctx->xbits & 15;
+  if (g.st_in) {
+    const long long rows = (long long)g.Mb * TILE_M;
+    HY3D_CUDA(ctx, ctx->ln_mr.reserve((size_t)rows * sizeof(float2)));
+    gd.ln_mr = ctx->ln_mr.as<float2>();
+    k_finish_stats<<<(unsigned)ceil_div64(rows, 256), 256, 0, ctx->stream>>>(g.st_in, g.st_slots, g.st_np, g.ln_eps, rows, ctx->ln_mr.as<float2>());
+    ctx->launches++;
+  }
   k_gemm_tc<EPI><<<grid, GEMM_THREADS, GEMM_SMEM, ctx->stream>>>(gd);
   HY3D_LAUNCH_CHECK(ctx);
   return 0;
@@ -837,20 +872,20 @@ __global__ void k_rows_to_t16_split(const float* __restrict__ src, int M, int K,
 }  // namespace
 
 namespace {
-// per-row (mean, M2) of fp32 rows [M, K] in the slot format of GemmTC::st_in: slot s covers columns [128 s, 128 s + 128)
+// per-row (mean, M2) of fp32 rows [M, K] in the slot format of GemmTC::st_in: slot s covers columns [64 s, 64 s + 64)
 __global__ void k_row_slot_stats(const float* __restrict__ src, int M, int K, float* __restrict__ st) {
   const long long wi = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31, S = K / 128;
+  const int lane = threadIdx.x & 31, S = K / ST_COLS;
   const long long rows_p = (long long)((M + 127) / 128) * 128;
   if (wi >= rows_p * S) return;
   const long long row = wi / S; const int slot = (int)(wi % S);
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (row < M) v = reinterpret_cast<const float4*>(src + row * K + slot * 128)[lane];
-  float sum = (v.x + v.y) + (v.z + v.w);
+  float2 v = make_float2(0.f, 0.f);
+  if (row < M) v = reinterpret_cast<const float2*>(src + row * K + slot * ST_COLS)[lane];
+  float sum = v.x + v.y;
   for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  const float mean = sum * (1.f / 128.f);
-  const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
-  float m2 = (a * a + b * b) + (c * c + d * d);
+  const float mean = sum * (1.f / ST_COLS);
+  const float a = v.x - mean, b = v.y - mean;
+  float m2 = a * a + b * b;
   for (int o = 16; o; o >>= 1) m2 += __shfl_xor_sync(0xffffffffu, m2, o);
   if (lane == 0) { st[(row * S + slot) * 2] = mean; st[(row * S + slot) * 2 + 1] = m2; }
 }
@@ -864,7 +899,7 @@ int hy3d_tc_project_kv(hy3d_ctx* ctx, const float* d_latents, int M) {
   if (!w.t_qp || !w.t_ckv3) return hy3d_fail(ctx, HY3D_ERR_UNSUPPORTED, "tcgen05 K/V projection unavailable for this decoder shape");
   KVState& kv = ctx->kv;
   const int W = w.W, H = w.H, LW = w.LW;
-  const int Mb = (M + 127) / 128, nkv = Mb, S = 2 * (W / BN);
+  const int Mb = (M + 127) / 128, nkv = Mb, S = W / ST_COLS;   // statistic slots (k_row_slot_stats / latents_proj epilogue)
   const size_t Mp = (size_t)Mb * 128;
   HY3D_CUDA(ctx, kv.k32.reserve((size_t)H * M * 64 * 4));
   HY3D_CUDA(ctx, kv.v32.reserve((size_t)H * M * 64 * 4));
@@ -896,7 +931,7 @@ int hy3d_tc_project_kv(hy3d_ctx* ctx, const float* d_latents, int M) {
   }
   GemmTC g{};
   g.Mb = Mb; g.A = a_kv; g.B = reinterpret_cast<const uint8_t*>(w.t_ckv3); g.KB = 3 * W / 64; g.N = 2 * W; g.Nb = 2 * W / BN; g.bias = w.bb_kv;
-  g.st_in = st; g.st_slots = S; g.st_np = 128; g.cs = w.cs_kv; g.ln_eps = 1e-6f;
+  g.st_in = st; g.st_slots = S; g.st_np = ST_COLS; g.cs = w.cs_kv; g.ln_eps = 1e-6f;
   g.Kout = kv.ktile.as<uint8_t>(); g.Vout = kv.vtile.as<uint8_t>(); g.nkv = nkv; g.Wq = W; g.part0 = 1;
   g.kn_w = w.kn_w; g.kn_b = w.kn_b; g.qk_norm = w.qk_norm ? 1 : 0; g.qscale = 1.f;
   g.K32 = kv.k32.as<float>(); g.V32T = kv.v32.as<float>(); g.Mtok = M;
@@ -910,7 +945,7 @@ static int decode_tc_impl(hy3d_ctx* ctx, const QuerySource& src_in, long long n,
   if (!w.t_qp)
     return hy3d_fail(ctx, HY3D_ERR_UNSUPPORTED, "tcgen05 path needs head_dim 64 and widths that are multiples of 256");
   const int W = w.W, H = w.H, R = w.R;
-  const int S = 2 * (W / BN);                                   // statistic slots per row (one per 128 output columns)
+  const int S = ST_PER_TILE * (W / BN);                         // statistic slots per row (one per 64 output columns)
   const long long CH = 131072;                                 // points per chunk (1024 tiles)
   const long long chmax = n < CH ? (n + 127) / 128 * 128 : CH;
   HY3D_CUDA(ctx, ctx->ws[2].reserve((size_t)chmax * W * 4));          // R32 residual stream
@@ -947,7 +982,7 @@ static int decode_tc_impl(hy3d_ctx* ctx, const QuerySource& src_in, long long n,
     // q = q_norm(c_q(ln_1 x0)) * scale * log2e      (ln_1 folded: raw x0 operand, statistics applied in the epilogue)
     g = GemmTC{}; g.Mb = Pb;
     g.A = tq; g.B = reinterpret_cast<const uint8_t*>(w.t_cq); g.KB = W / 64; g.N = W; g.Nb = W / BN; g.bias = w.bb_q; g.Tout = ta;
-    g.st_in = st1; g.st_slots = S; g.st_np = 128; g.cs = w.cs_q; g.ln_eps = 1e-6f;
+    g.st_in = st1; g.st_slots = S; g.st_np = ST_COLS; g.cs = w.cs_q; g.ln_eps = 1e-6f;
     g.qn_w = w.qn_w; g.qn_b = w.qn_b; g.qk_norm = w.qk_norm ? 1 : 0; g.qscale = rsqrtf((float)w.D) * LOG2E;
     if (int rc = launch_gemm<EPI_Q>(ctx, g, FAM_GEMM_CQ)) return rc;
     if (int rc = hy3d_debug_keep(ctx, 2, ta, (size_t)Pp * W * 2, 2, Pp, W)) return rc;
@@ -973,7 +1008,7 @@ static int decode_tc_impl(hy3d_ctx* ctx, const QuerySource& src_in, long long n,
     // h = gelu(c_fc(ln_3 x1))                      (ln_3 folded)
     g = GemmTC{}; g.Mb = Pb;
     g.A = ta; g.B = reinterpret_cast<const uint8_t*>(w.t_fc); g.KB = W / 64; g.N = W * R; g.Nb = W * R / BN; g.bias = w.bb_fc; g.Tout = th;
-    g.st_in = st3; g.st_slots = S; g.st_np = 128; g.cs = w.cs_fc; g.ln_eps = 1e-6f;
+    g.st_in = st3; g.st_slots = S; g.st_np = ST_COLS; g.cs = w.cs_fc; g.ln_eps = 1e-6f;
     if (int rc = launch_gemm<EPI_GELU>(ctx, g, FAM_GEMM_FC)) return rc;
     if (int rc = hy3d_debug_keep(ctx, 6, th, (size_t)Pp * W * R * 2, 2, Pp, W * R)) return rc;
     // x2 = x1 + c_proj(h): never stored (unless debugging) — only its row statistics and its dot with
@@ -985,7 +1020,7 @@ static int decode_tc_impl(hy3d_ctx* ctx, const QuerySource& src_in, long long n,
     if (int rc = hy3d_debug_keep(ctx, 7, x, (size_t)Pp * W * 4, 1, Pp, W)) return rc;
     float* outp = d_out + (out_mode == 0 ? p0 : 0);
     HY3D_PROF(ctx, FAM_HEAD);
-    k_head_final<<<Pb, 128, 0, ctx->stream>>>(stp, S, 128, w.ln_post ? 1 : 0, w.c12, src, P, outp, out_mode);
+    k_head_final<<<Pb, 128, 0, ctx->stream>>>(stp, S, ST_COLS, w.ln_post ? 1 : 0, w.c12, src, P, outp, out_mode);
     HY3D_LAUNCH_CHECK(ctx);
   }
   return 0;
@@ -1142,7 +1177,7 @@ extern "C" int hy3d_transformer_forward(hy3d_ctx* ctx, const float* d_z, int32_t
   if (!t.set) return hy3d_fail(ctx, HY3D_ERR_STATE, "transformer weights not set");
   if (M % 128) return hy3d_fail(ctx, HY3D_ERR_UNSUPPORTED, "token count must be a multiple of 128");
   HY3D_CUDA(ctx, cudaSetDevice(ctx->device));
-  const int W = t.W, H = t.H, R = t.R, E = t.E, Mb = M / 128, S = 2 * (W / BN);
+  const int W = t.W, H = t.H, R = t.R, E = t.E, Mb = M / 128, S = ST_PER_TILE * (W / BN);
   const size_t Mp = (size_t)M;
   HY3D_CUDA(ctx, t.x.reserve(Mp * W * 4));
   HY3D_CUDA(ctx, t.ta.reserve(Mp * 3 * W * 2));
@@ -1169,7 +1204,7 @@ extern "C" int hy3d_transformer_forward(hy3d_ctx* ctx, const float* d_z, int32_t
   for (int l = 0; l < t.L; ++l) {
     g = GemmTC{}; g.Mb = Mb;                                   // q, k, v = split(c_qkv(ln_1 x)), q/k norms
     g.A = ta; g.B = t.t_qkv[l]; g.KB = 3 * W / 64; g.N = 3 * W; g.Nb = 3 * W / BN; g.bias = t.bb_qkv[l];
-    g.st_in = stA; g.st_slots = S; g.st_np = 128; g.cs = t.cs_qkv[l]; g.ln_eps = 1e-6f;
+    g.st_in = stA; g.st_slots = S; g.st_np = ST_COLS; g.cs = t.cs_qkv[l]; g.ln_eps = 1e-6f;
     g.Tout = tq; g.Kout = t.kt.as<uint8_t>(); g.Vout = t.vt.as<uint8_t>(); g.nkv = Mb; g.Wq = W;
     g.qn_w = t.qn_w[l]; g.qn_b = t.qn_b[l]; g.kn_w = t.kn_w[l]; g.kn_b = t.kn_b[l]; g.qk_norm = t.qk_norm;
     g.qscale = rsqrtf(64.f) * LOG2E;
@@ -1185,7 +1220,7 @@ extern "C" int hy3d_transformer_forward(hy3d_ctx* ctx, const float* d_z, int32_t
     if (int rc = launch_gemm<EPI_RES>(ctx, g, FAM_KV)) return rc;
     g = GemmTC{}; g.Mb = Mb;                                   // h = gelu(c_fc(ln_2 x))
     g.A = ta; g.B = t.t_fc[l]; g.KB = 3 * W / 64; g.N = R * W; g.Nb = R * W / BN; g.bias = t.bb_fc[l];
-    g.st_in = stB; g.st_slots = S; g.st_np = 128; g.cs = t.cs_fc[l]; g.ln_eps = 1e-6f; g.Tout = th; g.split_out = 1;
+    g.st_in = stB; g.st_slots = S; g.st_np = ST_COLS; g.cs = t.cs_fc[l]; g.ln_eps = 1e-6f; g.Tout = th; g.split_out = 1;
     if (int rc = launch_gemm<EPI_GELU>(ctx, g, FAM_KV)) return rc;
     g = GemmTC{}; g.Mb = Mb;                                   // x += c_proj(h)
     g.A = th; g.B = t.t_proj2[l]; g.KB = 3 * R * W / 64; g.N = W; g.Nb = W / BN; g.bias = t.b_proj2[l];

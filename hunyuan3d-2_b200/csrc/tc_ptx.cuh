@@ -105,6 +105,25 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
                : "memory");
 }
 
+// ---- thread-block clusters -------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// all threads of all CTAs of the cluster (superset of __syncthreads)
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// global -> shared 1-D bulk copy delivered to the same CTA-relative offset in every CTA of `cta_mask`; each
+// destination CTA's mbarrier (same offset) receives the complete_tx
+__device__ __forceinline__ void bulk_g2s_multicast(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst_smem),
+      "l"(src), "r"(bytes), "r"(bar), "h"(cta_mask)
+      : "memory");
+}
+
 // ---- tcgen05 -------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
@@ -139,6 +158,13 @@ __device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uin
 // arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// the same arrival delivered to the mbarrier at this offset in every CTA of `cta_mask`
+__device__ __forceinline__ void mma_commit_multicast(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(cta_mask)
+               : "memory");
 }
 
 // instruction descriptor, .kind::f16: D=f32, A=B=f16, both K-major, dense

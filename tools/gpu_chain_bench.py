@@ -68,6 +68,15 @@ for bits in [int(b) for b in args.bits.split(",")]:
                 if f in flops:
                     d["tflops"] = round(flops[f] * args.points / (ms / args.reps) / 1e9, 1)
                 res["families"][f] = d
+        if bits & 8:        # SM clock during each GEMM family = cycles of CTA 0 / device time
+            tm = ctx.debug_timers()
+            fam_of = {0: "gemm_query_proj", 1: "gemm_c_q", 3: "gemm_c_fc"}
+            for epi, fam in fam_of.items():
+                if fam in res["families"] and tm[24 + epi]:
+                    res["families"][fam]["sm_mhz"] = round(tm[24 + epi] / args.reps / (res["families"][fam]["ms"] * 1e3))
+            if tm[26]:      # EPI_RES: c_proj + mlp_proj together
+                ms = res["families"]["gemm_c_proj"]["ms"] + res["families"]["gemm_mlp_proj"]["ms"]
+                res["families"]["gemm_mlp_proj"]["sm_mhz_res"] = round(tm[26] / args.reps / (ms * 1e3))
         if bits & 0x40:
             tm = ctx.debug_timers()
             res["softmax_clk_per_tile"] = [[round(tm[8 * a + i] / max(tm[8 * a + 7], 1)) for i in range(6)] for a in range(2)]
