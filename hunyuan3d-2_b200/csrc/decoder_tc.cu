@@ -24,6 +24,7 @@
 //   k_gemm_tc<GELU> c_fc + erf-GELU                              -> T16 h
 //   k_gemm_tc<RES>  mlp.c_proj + residual                        -> R32 x2
 //   k_head_tc       [ln_post] + output_proj                      -> logits (dense or scattered)
+#include <cuda.h>
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -36,7 +37,7 @@ constexpr int TILE_M = 128;
 constexpr int TILE_BYTES = 16384;          // 128 x 64 fp16
 constexpr int BN = 256;                    // GEMM N tile
 constexpr int BTILE_BYTES = BN * 128;      // 256 x 64 fp16
-constexpr int GEMM_STAGES = 4;
+constexpr int GEMM_STAGES = 5;            // 32 KB per stage and CTA: A tile + half of the B tile (+ 64 KB of output staging)
 constexpr int GEMM_THREADS = 640;          // warp0 producer, warp1 mma, warp2 tmem, warp3 idle, warps 4..19 epilogue
 constexpr int ST_PER_TILE = 4;             // row-statistic slots per 256-column tile (one per epilogue warp column quarter)
 constexpr int ST_COLS = BN / ST_PER_TILE;  // columns per slot (64)
@@ -123,39 +124,46 @@ __device__ __forceinline__ void store_t16_split(uint8_t* t0, uint8_t* t1, uint8_
 // ------------------------------------------------------------------------------------------
 // Persistent warp-specialised GEMM:  C[P, N] = A[P, K] * W[N, K]^T with a fused epilogue.
 // ------------------------------------------------------------------------------------------
-// Clusters of two CTAs work on two vertically adjacent 128 x 256 tiles (same weight tile): each CTA fetches its own A
-// tile and ONE HALF of the B tile, multicast into both CTAs' shared memory, so a tile costs 32 KB of L2 -> SM traffic
-// per k-block instead of 48 KB.  (Measured: with every CTA fetching all 48 KB the loads alone run at 85 % of the
-// MMA-only rate, and the K = 1024 GEMMs sit at the L2 -> SM bandwidth, not at the tensor pipe.)  A stage may be
-// refilled only when BOTH CTAs' MMAs have consumed it: the MMA warp's commit is multicast to both EMPTY barriers.
+// One MMA spans a CTA pair (cta_group::2): the pair computes a 256 x 256 tile, each CTA holding 128 rows of A, 128 of the
+// 256 B rows and its 128 x 256 accumulator.  Per k-block each SM moves 32 KB into and out of its shared memory instead
+// of 48 KB: with single-SM MMAs the TMA fills plus the operand reads already take ~190 B/clk of shared-memory
+// bandwidth and every epilogue load/store slowed the tensor pipe (full kernel 30 % slower than max(MMA-only,
+// epilogue-only)).  Barrier protocol (s = smem stage, acc = accumulator buffer):
+//   FULL(s)   local TMA bytes of this CTA's stage            -> leader MMA warp; peer's warp 1 relays it to the leader's PFULL(s)
+//   PFULL(s)  (leader) the peer's stage s is full             -> leader MMA warp
+//   EMPTY(s)  multicast tcgen05.commit of the leader          -> both producers
+//   TFULL(a)  multicast tcgen05.commit of the leader          -> both CTAs' epilogue warps
+//   TEMPTY(a) (leader) 16 local + 16 remote epilogue arrivals -> leader MMA warp
 template <int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(GemmTC g) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+k_gemm_tc(GemmTC g, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sA = smem;                                      // [STAGES][16 KB]
-  uint8_t* sB = smem + GEMM_STAGES * TILE_BYTES;           // [STAGES][32 KB]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GEMM_STAGES * (TILE_BYTES + BTILE_BYTES));
-  // bars: full[S], empty[S], tfull[2], tempty[2]
+  uint8_t* sA = smem;                                      // [STAGES][16 KB]  this CTA's 128 rows of A
+  uint8_t* sB = smem + GEMM_STAGES * TILE_BYTES;           // [STAGES][16 KB]  this CTA's 128 of the 256 B rows
+  uint8_t* sOut = smem + GEMM_STAGES * 2 * TILE_BYTES;     // [4 column quarters][16 KB]  fp16 output tiles staged for bulk stores
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + ST_PER_TILE * TILE_BYTES);
   const uint32_t bar0 = smem_u32(bars);
   auto FULL = [&](int s) { return bar0 + 8u * s; };
   auto EMPTY = [&](int s) { return bar0 + 8u * (GEMM_STAGES + s); };
-  auto TFULL = [&](int a) { return bar0 + 8u * (2 * GEMM_STAGES + a); };
-  auto TEMPTY = [&](int a) { return bar0 + 8u * (2 * GEMM_STAGES + 2 + a); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * GEMM_STAGES + 4);
+  auto PFULL = [&](int s) { return bar0 + 8u * (2 * GEMM_STAGES + s); };
+  auto TFULL = [&](int a) { return bar0 + 8u * (3 * GEMM_STAGES + a); };
+  auto TEMPTY = [&](int a) { return bar0 + 8u * (3 * GEMM_STAGES + 2 + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * GEMM_STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long clk0 = (g.dbg & 8) ? clock64() : 0;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < GEMM_STAGES; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 2); }
-    for (int a = 0; a < 2; ++a) { mbar_init(TFULL(a), 1); mbar_init(TEMPTY(a), 16); }
+    for (int s = 0; s < GEMM_STAGES; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); mbar_init(PFULL(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(TFULL(a), 1); mbar_init(TEMPTY(a), 32); }
     fence_barrier_init();
   }
-  if (warp == 2) { tmem_alloc(smem_u32(tmem_slot), 512); tmem_relinquish(); }
+  if (warp == 2) { tmem_alloc2(smem_u32(tmem_slot), 512); tmem_relinquish2(); }
   fence_before_sync();
-  cluster_sync();                      // the peer's barriers must exist before anything is multicast to them
+  cluster_sync();                      // the peer's barriers must exist before anything is signalled to them
   fence_after_sync();
   const uint32_t tmem = *tmem_slot;
-  // work item p of cluster c: tile pair (m-blocks 2 (p / Nb) + {0, 1}, n-block p % Nb); this CTA takes m-block + rank
+  // work item p of cluster c: tile pair (m-blocks 2 (p / Nb) + {0, 1}, n-block p % Nb); this CTA holds m-block + rank
   const int rank = (int)cluster_ctarank();
   const int npairs = ((g.Mb + 1) / 2) * g.Nb;
   const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
@@ -165,22 +173,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) k_g
     for (int p = cid; p < npairs; p += ncl) {
       int mb = 2 * (p / g.Nb) + rank; const int nb = p % g.Nb;
       if (mb >= g.Mb) mb = g.Mb - 1;   // odd tile count: the idle half still feeds its share of B (its results are dropped)
-      const uint8_t* a = g.A + (size_t)mb * g.KB * TILE_BYTES;
-      const uint8_t* b = g.B + (size_t)nb * g.KB * BTILE_BYTES + rank * (BTILE_BYTES / 2);
+      // operands as rows of 128 bytes (tensor maps tmA / tmB): A tile (mb, kb) = rows [(mb KB + kb) 128, +128),
+      // this CTA's half of B tile (nb, kb) = rows [(nb KB + kb) 256 + 128 rank, +128)
+      const int arow = mb * g.KB * 128, brow = nb * g.KB * 256 + rank * 128;
       for (int kb = 0; kb < g.KB; ++kb) {
         mbar_wait(EMPTY(s), ph ^ 1);
         if (elect_one()) {
-          mbar_arrive_expect_tx(FULL(s), TILE_BYTES + BTILE_BYTES);
-          bulk_g2s(smem_u32(sA + s * TILE_BYTES), a + (size_t)kb * TILE_BYTES, TILE_BYTES, FULL(s));
-          bulk_g2s_multicast(smem_u32(sB + s * BTILE_BYTES + rank * (BTILE_BYTES / 2)), b + (size_t)kb * BTILE_BYTES, BTILE_BYTES / 2,
-                             FULL(s), (uint16_t)3);
+          // both CTAs' copies complete on the LEADER's FULL(s) (64 KB per stage): no software relay on the critical path
+          if (rank == 0) mbar_arrive_expect_tx(FULL(s), 4 * TILE_BYTES);
+          tma2d_g2s_pair(smem_u32(sA + s * TILE_BYTES), &tmA, 0, arow + kb * 128, FULL(s));
+          tma2d_g2s_pair(smem_u32(sB + s * TILE_BYTES), &tmB, 0, brow + kb * 256, FULL(s));
         }
         __syncwarp();
         if (++s == GEMM_STAGES) { s = 0; ph ^= 1; }
       }
     }
+  } else if (warp == 1 && rank != 0) {
+    // peer CTA: the leader issues the pair's MMAs
   } else if (warp == 1) {
-    const uint32_t idesc = make_idesc_f16(TILE_M, BN);
+    const uint32_t idesc = make_idesc_f16(2 * TILE_M, BN);
     int s = 0; uint32_t ph = 0;
     int it = 0;
     for (int p = cid; p < npairs; p += ncl, ++it) {
@@ -193,13 +204,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) k_g
         mbar_wait(FULL(s), ph);
         fence_after_sync();
         const uint64_t ad = make_desc_sw128(smem_u32(sA + s * TILE_BYTES));
-        const uint64_t bd = make_desc_sw128(smem_u32(sB + s * BTILE_BYTES));
+        const uint64_t bd = make_desc_sw128(smem_u32(sB + s * TILE_BYTES));
         if (elect_one()) {
           if (!(g.dbg & 2))
 #pragma unroll
-            for (int k = 0; k < 4; ++k) mma_f16_ss(d, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
-          mma_commit_multicast(EMPTY(s), (uint16_t)3);
-          if (kb == g.KB - 1) mma_commit(TFULL(acc));
+            for (int k = 0; k < 4; ++k) mma2_f16_ss(d, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
+          mma2_commit_multicast(EMPTY(s), (uint16_t)3);
+          if (kb == g.KB - 1) mma2_commit_multicast(TFULL(acc), (uint16_t)3);
         }
         __syncwarp();
         if (++s == GEMM_STAGES) { s = 0; ph ^= 1; }
@@ -218,7 +229,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) k_g
       const uint32_t aph = (it >> 1) & 1;
       mbar_wait(TFULL(acc), aph);
       fence_after_sync();
-      if ((g.dbg & 1) || mb >= g.Mb) { fence_before_sync(); __syncwarp(); if (lane == 0) mbar_arrive(TEMPTY(acc)); continue; }
+      if ((g.dbg & 1) || mb >= g.Mb) {
+        fence_before_sync(); __syncwarp();
+        if (lane == 0) { if (rank == 0) mbar_arrive(TEMPTY(acc)); else mbar_arrive_remote(TEMPTY(acc), 0); }
+        continue;
+      }
       const uint32_t tcol = tmem + acc * BN + cq * 64 + ((uint32_t)(q * 32) << 16);
       const int c0 = nb * BN + cq * 64;     // first global column of this warp's quarter
       float ln_mean = 0.f, ln_rstd = 1.f;
@@ -244,6 +259,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) k_g
             x[4 * i4] = a0 + bv.x; x[4 * i4 + 1] = a1 + bv.y; x[4 * i4 + 2] = a2 + bv.z; x[4 * i4 + 3] = a3 + bv.w;
           }
         }
+      };
+      // fp16 T16 output tile (128 rows x 64 columns = this column quarter) of the tile: the quarter's four warps write
+      // their rows into the staging tile, then one thread hands the 16 KB to the bulk-copy engine
+      uint8_t* sOq = sOut + cq * TILE_BYTES;
+      auto stage_begin = [&]() {          // the previous bulk store must have finished reading the staging tile
+        if (q == 0 && lane == 0) bulk_wait_read();
+        named_bar_sync(1 + cq, 128);
+      };
+      auto stage_chunk = [&](int ch, const float* x) {
+#pragma unroll
+        for (int c16 = 0; c16 < 4; ++c16) store_t16_chunk(sOq, r, ch * 4 + c16, x + 8 * c16);
+      };
+      auto stage_flush = [&](uint8_t* gtile) {
+        fence_proxy_async_smem();
+        named_bar_sync(1 + cq, 128);
+        if (q == 0 && lane == 0) bulk_s2g(gtile, smem_u32(sOq), TILE_BYTES);
       };
       if constexpr (EPI == EPI_Q || EPI == EPI_QF32 || EPI == EPI_QKV) {
         // this warp's 64 columns are exactly one head: per-head LayerNorm (q_norm / k_norm) in two passes over TMEM
@@ -319,8 +350,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) k_g
             }
             uint8_t* tile = part == 1 ? g.Kout + ((size_t)h * g.nkv + mb) * TILE_BYTES
                                       : g.Tout + ((size_t)mb * ((EPI == EPI_QKV ? g.Wq : g.N) / 64) + h) * TILE_BYTES;
-#pragma unroll
-            for (int c16 = 0; c16 < 4; ++c16) store_t16_chunk(tile, r, ch * 4 + c16, x + 8 * c16);
+            if (ch == 0) stage_begin();
+            stage_chunk(ch, x);
+            if (ch == 1) stage_flush(tile);
           }
         }
       } else {
@@ -350,8 +382,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) k_g
               for (int c16 = 0; c16 < 4; ++c16)
                 store_t16_split(tile, tile + (size_t)KBn * TILE_BYTES, tile + (size_t)2 * KBn * TILE_BYTES, r, ch * 4 + c16, x + 8 * c16);
             } else {
-#pragma unroll
-              for (int c16 = 0; c16 < 4; ++c16) store_t16_chunk(tile, r, ch * 4 + c16, x + 8 * c16);
+              if (ch == 0) stage_begin();
+              stage_chunk(ch, x);
+              if (ch == 1) stage_flush(tile);
             }
           } else {
             // R32: [mb][c/4][row][4]
@@ -375,8 +408,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) k_g
                 for (int c16 = 0; c16 < 4; ++c16)
                   store_t16_split(tile, tile + (size_t)KBn * TILE_BYTES, tile + (size_t)2 * KBn * TILE_BYTES, r, ch * 4 + c16, x + 8 * c16);
               } else {
-#pragma unroll
-                for (int c16 = 0; c16 < 4; ++c16) store_t16_chunk(tile, r, ch * 4 + c16, x + 8 * c16);
+                if (ch == 0) stage_begin();
+                stage_chunk(ch, x);
+                if (ch == 1) stage_flush(tile);
               }
             }
             if (g.st_out) {
@@ -412,16 +446,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) k_g
       }
       fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(TEMPTY(acc));
+      if (lane == 0) { if (rank == 0) mbar_arrive(TEMPTY(acc)); else mbar_arrive_remote(TEMPTY(acc), 0); }
     }
   }
+  if (warp >= 4 && (warp & 3) == 0 && lane == 0) bulk_wait_all();   // staged output tiles have reached global memory
   fence_before_sync();
   cluster_sync();                      // the peer may still be signalling this CTA's barriers
-  if (warp == 2) tmem_dealloc(tmem, 512);
+  if (warp == 2) tmem_dealloc2(tmem, 512);
   if ((g.dbg & 8) && threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(&hy3d_tm[24 + EPI], (unsigned long long)(clock64() - clk0));   // SM cycles of this launch
 }
 
-constexpr size_t GEMM_SMEM = 1024 + GEMM_STAGES * (TILE_BYTES + BTILE_BYTES) + 256;
+constexpr size_t GEMM_SMEM = 1024 + GEMM_STAGES * 2 * TILE_BYTES + ST_PER_TILE * TILE_BYTES + 256;
 
 #include "attention_tc.cuh"
 
@@ -675,6 +710,30 @@ __global__ void k_build_kv(const float* __restrict__ k32, const float* __restric
   }
 }
 
+// Tensor map over an operand image viewed as rows of 128 bytes (every UMMA tile is 128 or 256 such rows, already
+// swizzled in memory): box = 128 rows x 128 bytes = one 16 KB tile, no hardware swizzle.  cuTensorMapEncodeTiled comes
+// from the driver through the runtime (no link-time libcuda dependency).
+int make_rows_map(hy3d_ctx* ctx, CUtensorMap* m, const void* base, uint64_t rows) {
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_fn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    HY3D_CUDA(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (!fn || q != cudaDriverEntryPointSuccess) return hy3d_fail(ctx, HY3D_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
+    encode = reinterpret_cast<encode_fn>(fn);
+  }
+  const cuuint64_t dims[2] = {128, rows};
+  const cuuint64_t strides[1] = {128};
+  const cuuint32_t box[2] = {128, 128};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = encode(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return hy3d_fail(ctx, HY3D_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
 // (mean, rstd) per row from the S partial (mean, M2) slots a producer epilogue wrote: once per row here, instead of
 // S strided loads per row in every consumer tile (which made the consumer epilogues LSU-bound)
 __global__ void k_finish_stats(const float* __restrict__ st, int S, int n_p, float eps, long long rows, float2* __restrict__ out) {
@@ -708,7 +767,10 @@ int launch_gemm(hy3d_ctx* ctx, const GemmTC& g, int fam) {
     k_finish_stats<<<(unsigned)ceil_div64(rows, 256), 256, 0, ctx->stream>>>(g.st_in, g.st_slots, g.st_np, g.ln_eps, rows, ctx->ln_mr.as<float2>());
     ctx->launches++;
   }
-  k_gemm_tc<EPI><<<grid, GEMM_THREADS, GEMM_SMEM, ctx->stream>>>(gd);
+  CUtensorMap tmA, tmB;
+  if (int rc = make_rows_map(ctx, &tmA, g.A, (uint64_t)g.Mb * g.KB * 128)) return rc;
+  if (int rc = make_rows_map(ctx, &tmB, g.B, (uint64_t)g.Nb * g.KB * 256)) return rc;
+  k_gemm_tc<EPI><<<grid, GEMM_THREADS, GEMM_SMEM, ctx->stream>>>(gd, tmA, tmB);
   HY3D_LAUNCH_CHECK(ctx);
   return 0;
 }

@@ -105,6 +105,17 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
                : "memory");
 }
 
+// shared -> global 1-D bulk copy (async proxy, bulk-group completion): whole 16 KB tiles leave through the copy engine
+// instead of 32-way scattered 16-byte st.global through L1
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// all bulk groups of this thread have finished READING their shared-memory source
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+
 // ---- thread-block clusters -------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -122,6 +133,47 @@ __device__ __forceinline__ void bulk_g2s_multicast(uint32_t dst_smem, const void
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst_smem),
       "l"(src), "r"(bytes), "r"(bar), "h"(cta_mask)
       : "memory");
+}
+
+// arrive (release, cluster scope) on the mbarrier at the same offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar), "r"(cta)
+      : "memory");
+}
+// wait with cluster-scope acquire: pairs with mbar_arrive_remote from the peer CTA
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+#if HY3D_TC_WATCHDOG
+    if ((++spins & 0xffu) != 0) continue;
+    const uint32_t limit = (*(volatile int*)&hy3d_wd[0]) ? (1u << 8) : (1u << 22);
+    if (spins >= limit) {
+      if (atomicExch(&hy3d_wd[0], 1) == 0) {
+        hy3d_wd[1] = (int)blockIdx.x; hy3d_wd[2] = (int)threadIdx.x; hy3d_wd[3] = (int)bar; hy3d_wd[4] = (int)parity;
+      }
+      return;
+    }
+#endif
+  }
+}
+
+// shared::cluster address of the same offset in CTA `cta`
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
+  return r;
 }
 
 // ---- tcgen05 -------------------------------------------------------------------------------
@@ -164,6 +216,41 @@ __device__ __forceinline__ void mma_commit(uint32_t bar) {
 __device__ __forceinline__ void mma_commit_multicast(uint32_t bar, uint16_t cta_mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
                "h"(cta_mask)
+               : "memory");
+}
+
+// ---- CTA-pair (cta_group::2) forms: one MMA spans two SMs (M = 256: 128 rows per CTA; each CTA supplies its A rows
+// and half of the B rows from its own shared memory; accumulators in both CTAs' TMEM at the same address).
+// Issued by the leader CTA (cluster rank 0) only; alloc / dealloc by the same warp id in BOTH CTAs.
+__device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void mma2_f16_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma2_commit_multicast(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(cta_mask)
+               : "memory");
+}
+
+// 2-D tensor-map TMA load of a CTA pair: the bytes land in THIS CTA's shared memory, the complete_tx goes to the
+// mbarrier at the same offset in the pair's leader (even) CTA — clearing the peer bit of the shared-window address
+__device__ __forceinline__ void tma2d_g2s_pair(uint32_t dst_smem, const void* tmap, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                   dst_smem),
+               "l"(tmap), "r"(c0), "r"(c1), "r"(bar & 0xFEFFFFFFu)
                : "memory");
 }
 

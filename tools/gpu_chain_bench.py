@@ -18,6 +18,7 @@ ap.add_argument("--model", default="full")
 ap.add_argument("--points", type=int, default=524288)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--tag", default="")
+ap.add_argument("--no-pre", action="store_true", help="skip the transformer / K/V timings (short kernel sequence for ncu)")
 ap.add_argument("--bits", default="0", help="comma list of experiment bit sets")
 ap.add_argument("--poly", default="0", help="comma list of attn_poly values")
 args = ap.parse_args()
@@ -39,10 +40,11 @@ def timed(fn, reps=5):
         fn()
     b.record(); torch.cuda.synchronize()
     return a.elapsed_time(b) / reps
-pre = {"transformer_ms": round(timed(lambda: vae(z)), 3)}
-ctx.debug_experiment(0x10000, 0); pre["prepare_kv_simt_ms"] = round(timed(lambda: ctx.prepare_kv(lat[0])), 3)
-ctx.debug_experiment(0, 0); pre["prepare_kv_tc_ms"] = round(timed(lambda: ctx.prepare_kv(lat[0])), 3)
-print(json.dumps(pre), flush=True)
+if not args.no_pre:
+    pre = {"transformer_ms": round(timed(lambda: vae(z)), 3)}
+    ctx.debug_experiment(0x10000, 0); pre["prepare_kv_simt_ms"] = round(timed(lambda: ctx.prepare_kv(lat[0])), 3)
+    ctx.debug_experiment(0, 0); pre["prepare_kv_tc_ms"] = round(timed(lambda: ctx.prepare_kv(lat[0])), 3)
+    print(json.dumps(pre), flush=True)
 M, Wd, R = cfg.num_latents, cfg.width, 4
 flops = {"gemm_query_proj": 2 * 51 * Wd, "gemm_c_q": 2 * Wd * Wd, "attention": 4 * M * Wd, "gemm_c_proj": 2 * Wd * Wd,
          "gemm_c_fc": 2 * R * Wd * Wd, "gemm_mlp_proj": 2 * R * Wd * Wd}
