@@ -71,15 +71,42 @@ struct GemmTC {
   int dbg;               // HY3D_DBG experiment bits: 1 no epilogue, 2 no MMA, 4 no epilogue stores
 };
 
-// merge S partial (mean, M2) pairs of n_p samples each -> (mean, rstd)
-__device__ __forceinline__ void merge_row_stats(const float* __restrict__ st, int S, int stride, int n_p, float eps, float& mean,
-                                                float& rstd) {
-  float ms = 0.f;
-  for (int i = 0; i < S; ++i) ms += __ldg(st + i * stride);
+// merge S partial (mean, M2) pairs of n_p samples each -> (mean, rstd)   (Chan et al., deterministic order)
+// `st` = S records of `stride` floats (mean, M2[, dot]); record i at st + i * stride.  The whole row record block
+// (S * stride floats, 16-byte aligned) is read with 128-bit loads: a thread per row would otherwise issue S * stride
+// scalar loads that no warp-mate shares a sector with.
+template <int kStride>
+__device__ __forceinline__ void merge_row_stats(const float* __restrict__ st, int S, int n_p, float eps, float& mean, float& rstd,
+                                                float* dot = nullptr) {
+  constexpr int kMaxS = 16;                       // widths up to 1024 (64-column slots) take the vector path
+  if (S <= kMaxS && ((S * kStride) & 3) == 0) {
+    float v[kMaxS * kStride];
+#pragma unroll
+    for (int i = 0; i < kMaxS * kStride / 4; ++i)
+      if (4 * i < S * kStride) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(st) + i);
+        v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+      }
+    float ms = 0.f, d = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxS; ++i)
+      if (i < S) { ms += v[i * kStride]; if (kStride == 3) d += v[i * kStride + kStride - 1]; }
+    mean = ms / (float)S;
+    float M2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxS; ++i)
+      if (i < S) { const float dd = v[i * kStride] - mean; M2 += v[i * kStride + 1] + (float)n_p * dd * dd; }
+    rstd = rsqrtf(M2 / (float)(S * n_p) + eps);
+    if (dot) *dot = d;
+    return;
+  }
+  float ms = 0.f, d = 0.f;
+  for (int i = 0; i < S; ++i) { ms += __ldg(st + i * kStride); if (kStride == 3) d += __ldg(st + i * kStride + 2); }
   mean = ms / (float)S;
   float M2 = 0.f;
-  for (int i = 0; i < S; ++i) { const float d = __ldg(st + i * stride) - mean; M2 += __ldg(st + i * stride + 1) + (float)n_p * d * d; }
+  for (int i = 0; i < S; ++i) { const float dd = __ldg(st + i * kStride) - mean; M2 += __ldg(st + i * kStride + 1) + (float)n_p * dd * dd; }
   rstd = rsqrtf(M2 / (float)(S * n_p) + eps);
+  if (dot) *dot = d;
 }
 
 // exact-erf GELU (reference attention_blocks.py:177) without erff's two divergent branches:
@@ -593,17 +620,9 @@ __global__ void __launch_bounds__(128) k_head_final(const float* __restrict__ st
                                                      QuerySource src, long long n, float* __restrict__ out, int out_mode) {
   const long long qi = (long long)blockIdx.x * TILE_M + threadIdx.x;
   if (qi >= n) return;
-  const float* s = st + (size_t)qi * S * 3;
-  float dot = 0.f;
-  for (int i = 0; i < S; ++i) dot += __ldg(s + 3 * i + 2);
-  float v;
-  if (ln_post) {
-    float mean, rstd;
-    merge_row_stats(s, S, 3, n_p, 1e-5f, mean, rstd);
-    v = rstd * (dot - mean * __ldg(c12)) + __ldg(c12 + 1);
-  } else {
-    v = dot + __ldg(c12 + 1);
-  }
+  float mean, rstd, dot;
+  merge_row_stats<3>(st + (size_t)qi * S * 3, S, n_p, 1e-5f, mean, rstd, &dot);
+  const float v = ln_post ? rstd * (dot - mean * __ldg(c12)) + __ldg(c12 + 1) : dot + __ldg(c12 + 1);
   long long oi = qi;
   if (out_mode == 1) { oi = src.index[qi]; if (oi < 0) return; }
   out[oi] = v;
@@ -740,7 +759,7 @@ __global__ void k_finish_stats(const float* __restrict__ st, int S, int n_p, flo
   const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= rows) return;
   float mean, rstd;
-  merge_row_stats(st + row * S * 2, S, 2, n_p, eps, mean, rstd);
+  merge_row_stats<2>(st + row * S * 2, S, n_p, eps, mean, rstd);
   out[row] = make_float2(mean, rstd);
 }
 
