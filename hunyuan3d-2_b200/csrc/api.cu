@@ -108,6 +108,7 @@ int hy3d_create(int device, void* cuda_stream, hy3d_ctx** out) {
   ctx->num_sms = prop.multiProcessorCount;
   if (const char* e = getenv("HY3D_ATTN_POLY")) ctx->attn_poly = atoi(e);
   if (const char* e = getenv("HY3D_DBG")) ctx->xbits = atoi(e);
+  if (const char* e = getenv("HY3D_CHUNK")) { long long c = atoll(e); if (c >= 256) ctx->chunk_points = c / 256 * 256; }
   if (cudaMallocHost(&ctx->pinned, 4096) != cudaSuccess) { delete ctx; return HY3D_ERR_CUDA; }
   *out = ctx;
   return HY3D_OK;

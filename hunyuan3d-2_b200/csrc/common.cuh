@@ -47,6 +47,7 @@ struct DecoderWeights {
   const float *cs_q, *bb_q, *cs_fc, *bb_fc, *dotw, *c12;
   const __half *t_ckv3, *t_lp3;                           // c_kv (ln_2 folded, [k | v] rows) and latents_proj, 3-term split
   const float *cs_kv, *bb_kv;
+  const __half* t_cpx; const float* b_cpx;               // [c_proj | query_proj] K-concatenated image and b_o + b_qp (fused residual)
   const __half* t_cq3;
   float attn_bound = 0.f;              // upper bound of |q.k| scale log2e from the q/k norm weights (inf without qk_norm)
   bool attn_fast = false;              // bound <= 14: the attention kernel without a running maximum is exact (attention_tc.cuh)                                    // c_q split [W_hi | W_hi | W_lo], K = 3W (fp32-grade q for KV selection)
@@ -125,6 +126,7 @@ struct hy3d_ctx {
   // diagnostics: per-stage activations of the last decoded chunk (hy3d_debug_retain / hy3d_debug_fetch)
   int attn_poly = 1;                  // of every 8 attention exponentials, how many run on the FMA pipe (HY3D_ATTN_POLY: 0..4; bounded-score kernel)
   int debug_retain = 0;
+  long long chunk_points = 131072;    // decoder chunk (HY3D_CHUNK): activations of one chunk are what the stages hand over through L2 / HBM
   int xbits = 0;                      // HY3D_DBG: experiment bits for tools/gpu_chain_bench.py (results are garbage when set)
   DevBuf dbg[8];
   int dbg_layout[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // 0 row-major fp32, 1 R32, 2 T16

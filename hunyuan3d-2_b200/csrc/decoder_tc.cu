@@ -2,28 +2,29 @@
 // attention_blocks.py:483-493) for batches of query points, fp16 operands with
 // fp32 accumulation in tensor memory.
 //
-// Memory layout (all chosen so that every operand tile is ONE contiguous 16/32 KB block that a
-// single 1-D bulk async copy (cp.async.bulk, SASS UBLKCP) drops into shared memory already in the
-// 128-byte-swizzled K-major form the UMMA descriptors expect — no tensor maps, no strided TMA):
+// Memory layout: every operand tile is ONE contiguous 16/32 KB block already in the 128-byte-swizzled K-major
+// form the UMMA descriptors expect, so a single copy drops it into shared memory — a 1-D bulk copy (cp.async.bulk,
+// SASS UBLKCP) in the attention kernel, a tensor-map TMA over "rows of 128 bytes" (UTMALDG) in the CTA-pair GEMM:
 //   "T16"  fp16 activations  [P/128][K/64][128 rows x 64 cols, SW128]        (16 KB tiles)
 //   "B16"  fp16 weights      [N/256][K/64][256 rows x 64 cols, SW128]        (32 KB tiles)
 //   "R32"  fp32 residual     [P/128][N/4][128 rows][4]   (row-per-thread epilogues read/write 512 B
 //                                                          contiguous per warp instruction)
 //   K      fp16 [group][head][M/128][128 tok x 64, SW128]      V^T fp16 [group][head][M/128][2][64 d x 64 tok, SW128]
 //
-// Stage chain per chunk of points (one launch each, activations through HBM/L2; the chain is
-// compute-bound: ~30 KB/point of traffic vs 33.7 MFLOP/point):
-//   k_embed_tc      Fourier features, fp16 hi/lo split          -> T16 [.,3]
-//   k_gemm_tc<X0>   query_proj (3-term split fp16 = ~fp32)      -> R32 x0
-//   k_ln_tc         ln_1                                         -> T16
-//   k_gemm_tc<Q>    c_q, per-head q_norm, *scale*log2e           -> T16 q (k-block == head)
-//   k_attn_fast /   softmax(q k^T) v, 2 heads in flight per CTA (attention_tc.cuh)  -> T16
-//   k_attn_tc
-//   k_gemm_tc<RES>  c_proj + residual                            -> R32 x1
-//   k_ln_tc         ln_3                                         -> T16
-//   k_gemm_tc<GELU> c_fc + erf-GELU                              -> T16 h
-//   k_gemm_tc<RES>  mlp.c_proj + residual                        -> R32 x2
-//   k_head_tc       [ln_post] + output_proj                      -> logits (dense or scattered)
+// Stage chain per chunk of 131072 points (one launch each, activations through HBM/L2; the chain is
+// compute-bound: ~30 KB/point of traffic vs 33.7 MFLOP/point).  The three LayerNorms never run as kernels: ln_1 / ln_3
+// are folded into the consuming GEMM (raw operand, gamma in the weights, per-row statistics from the producer's
+// epilogue), ln_post into the head:
+//   k_embed_tc       Fourier features, fp16 hi/lo split                          -> T16 [., 3]
+//   k_gemm_tc<X0>    query_proj (3-term split fp16 = ~fp32)                       -> R32 x0, T16 raw x0, row stats
+//   k_gemm_tc<Q>     c_q (ln_1 folded), per-head q_norm, * scale * log2e          -> T16 q (k-block == head)
+//   k_attn_fast / k_attn_tc   softmax(q k^T) v, 2 heads in flight per CTA (attention_tc.cuh)  -> T16
+//   k_gemm_tc<RES>   c_proj + residual                                           -> R32 x1, T16 raw x1, row stats
+//   k_gemm_tc<GELU>  c_fc (ln_3 folded) + erf-GELU                                -> T16 h
+//   k_gemm_tc<RES>   mlp.c_proj + residual: only row stats + dot with gamma_post * w_out leave the kernel
+//   k_head_final     [ln_post] + output_proj from those statistics               -> logits (dense or scattered)
+// (k_finish_stats merges a producer's per-64-column partial statistics once per row before each folded GEMM;
+//  k_ln_tc is the unfolded LayerNorm, used by the fp32-grade q of the FlashVDM token selection.)
 #include <cuda.h>
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -46,7 +47,9 @@ constexpr float LOG2E = 1.4426950408889634f;
 enum { EPI_X0 = 0, EPI_Q = 1, EPI_RES = 2, EPI_GELU = 3, EPI_QF32 = 4, EPI_QKV = 5 };
 
 struct GemmTC {
-  const uint8_t* A;      // T16 tiles [Mb][KB]
+  const uint8_t* A;      // T16 tiles [Mb][KB]  (k-blocks 0 .. KB1-1 when a second operand is concatenated along K)
+  const uint8_t* A2;     // optional second A operand, T16 tiles [Mb][KB - KB1]: k-blocks KB1 .. KB-1 (K-concatenated GEMM)
+  int KB1;               // k-blocks taken from A (0 = all)
   const uint8_t* B;      // B16 tiles [Nb][KB]
   int Mb, Nb, KB, N;
   const float* bias;     // [N] or null
@@ -163,7 +166,7 @@ __device__ __forceinline__ void store_t16_split(uint8_t* t0, uint8_t* t1, uint8_
 //   TEMPTY(a) (leader) 16 local + 16 remote epilogue arrivals -> leader MMA warp
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
-k_gemm_tc(GemmTC g, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB) {
+k_gemm_tc(GemmTC g, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;                                      // [STAGES][16 KB]  this CTA's 128 rows of A
@@ -202,13 +205,15 @@ k_gemm_tc(GemmTC g, const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (mb >= g.Mb) mb = g.Mb - 1;   // odd tile count: the idle half still feeds its share of B (its results are dropped)
       // operands as rows of 128 bytes (tensor maps tmA / tmB): A tile (mb, kb) = rows [(mb KB + kb) 128, +128),
       // this CTA's half of B tile (nb, kb) = rows [(nb KB + kb) 256 + 128 rank, +128)
-      const int arow = mb * g.KB * 128, brow = nb * g.KB * 256 + rank * 128;
+      const int kb1 = g.KB1 ? g.KB1 : g.KB;
+      const int arow = mb * kb1 * 128, a2row = mb * (g.KB - kb1) * 128, brow = nb * g.KB * 256 + rank * 128;
       for (int kb = 0; kb < g.KB; ++kb) {
         mbar_wait(EMPTY(s), ph ^ 1);
         if (elect_one()) {
           // both CTAs' copies complete on the LEADER's FULL(s) (64 KB per stage): no software relay on the critical path
           if (rank == 0) mbar_arrive_expect_tx(FULL(s), 4 * TILE_BYTES);
-          tma2d_g2s_pair(smem_u32(sA + s * TILE_BYTES), &tmA, 0, arow + kb * 128, FULL(s));
+          if (kb < kb1) tma2d_g2s_pair(smem_u32(sA + s * TILE_BYTES), &tmA, 0, arow + kb * 128, FULL(s));
+          else tma2d_g2s_pair(smem_u32(sA + s * TILE_BYTES), &tmA2, 0, a2row + (kb - kb1) * 128, FULL(s));
           tma2d_g2s_pair(smem_u32(sB + s * TILE_BYTES), &tmB, 0, brow + kb * 256, FULL(s));
         }
         __syncwarp();
@@ -221,15 +226,20 @@ k_gemm_tc(GemmTC g, const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const uint32_t idesc = make_idesc_f16(2 * TILE_M, BN);
     int s = 0; uint32_t ph = 0;
     int it = 0;
+    long long tw0 = 0, tw[3] = {0, 0, 0};          // (experiment bit 8) cycles: wait TEMPTY, wait FULL, issue
+    const bool tmr = (g.dbg & 8) && blockIdx.x == 0;
     for (int p = cid; p < npairs; p += ncl, ++it) {
       const int acc = it & 1;
       const uint32_t aph = (it >> 1) & 1;
+      if (tmr) tw0 = clock64();
       mbar_wait(TEMPTY(acc), aph ^ 1);
       fence_after_sync();
+      if (tmr) { const long long t_ = clock64(); tw[0] += t_ - tw0; tw0 = t_; }
       const uint32_t d = tmem + acc * BN;
       for (int kb = 0; kb < g.KB; ++kb) {
         mbar_wait(FULL(s), ph);
         fence_after_sync();
+        if (tmr) { const long long t_ = clock64(); tw[1] += t_ - tw0; tw0 = t_; }
         const uint64_t ad = make_desc_sw128(smem_u32(sA + s * TILE_BYTES));
         const uint64_t bd = make_desc_sw128(smem_u32(sB + s * TILE_BYTES));
         if (elect_one()) {
@@ -240,9 +250,11 @@ k_gemm_tc(GemmTC g, const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (kb == g.KB - 1) mma2_commit_multicast(TFULL(acc), (uint16_t)3);
         }
         __syncwarp();
+        if (tmr) { const long long t_ = clock64(); tw[2] += t_ - tw0; tw0 = t_; }
         if (++s == GEMM_STAGES) { s = 0; ph ^= 1; }
       }
     }
+    if (tmr && lane == 0) { for (int i = 0; i < 3; ++i) atomicAdd(&hy3d_tm[16 + i], (unsigned long long)tw[i]); atomicAdd(&hy3d_tm[19], (unsigned long long)it); }
   } else if (warp >= 4) {
     // ---------------- epilogue: 16 warps = 4 TMEM lane quadrants x 4 column quarters of 64 ----------------
     // (four warps per scheduler: the TMEM-load -> constants -> math -> store chain of one warp hides behind the others)
@@ -250,12 +262,16 @@ k_gemm_tc(GemmTC g, const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int cq = (warp - 4) >> 2;         // 64-column quarter of the 256-wide tile
     const int r = q * 32 + lane;            // row inside the tile
     int it = 0;
+    long long te0 = 0, te[2] = {0, 0};              // (experiment bit 8) cycles: wait TFULL, work
+    const bool tmr = (g.dbg & 8) && blockIdx.x == 0 && warp == 4;
     for (int p = cid; p < npairs; p += ncl, ++it) {
       const int mb = 2 * (p / g.Nb) + rank, nb = p % g.Nb;
       const int acc = it & 1;
       const uint32_t aph = (it >> 1) & 1;
+      if (tmr) { const long long t_ = clock64(); if (it) te[1] += t_ - te0; te0 = t_; }
       mbar_wait(TFULL(acc), aph);
       fence_after_sync();
+      if (tmr) { const long long t_ = clock64(); te[0] += t_ - te0; te0 = t_; }
       if ((g.dbg & 1) || mb >= g.Mb) {
         fence_before_sync(); __syncwarp();
         if (lane == 0) { if (rank == 0) mbar_arrive(TEMPTY(acc)); else mbar_arrive_remote(TEMPTY(acc), 0); }
@@ -420,7 +436,7 @@ k_gemm_tc(GemmTC g, const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int i4 = 0; i4 < 8; ++i4) {
               float4 o = make_float4(x[4 * i4], x[4 * i4 + 1], x[4 * i4 + 2], x[4 * i4 + 3]);
               const size_t idx = base + (size_t)i4 * TILE_M;
-              if constexpr (EPI == EPI_RES) {
+              if (EPI == EPI_RES && g.Rin) {
                 const float4 rr = __ldg(reinterpret_cast<const float4*>(g.Rin) + idx);
                 o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
                 x[4 * i4] = o.x; x[4 * i4 + 1] = o.y; x[4 * i4 + 2] = o.z; x[4 * i4 + 3] = o.w;
@@ -475,6 +491,7 @@ k_gemm_tc(GemmTC g, const __grid_constant__ CUtensorMap tmA, const __grid_consta
       __syncwarp();
       if (lane == 0) { if (rank == 0) mbar_arrive(TEMPTY(acc)); else mbar_arrive_remote(TEMPTY(acc), 0); }
     }
+    if (tmr && lane == 0) { te[1] += clock64() - te0; atomicAdd(&hy3d_tm[20], (unsigned long long)te[0]); atomicAdd(&hy3d_tm[21], (unsigned long long)te[1]); }
   }
   if (warp >= 4 && (warp & 3) == 0 && lane == 0) bulk_wait_all();   // staged output tiles have reached global memory
   fence_before_sync();
@@ -570,50 +587,6 @@ __global__ void __launch_bounds__(128) k_ln_tc(const float* __restrict__ R, int 
   }
 }
 
-// [ln_post] + output_proj (attention_blocks.py:490-492): R32 -> logits
-__global__ void __launch_bounds__(128) k_head_tc(const float* __restrict__ R, int N, const float* __restrict__ gam,
-                                                  const float* __restrict__ bet, const float* __restrict__ wout,
-                                                  const float* __restrict__ bout, QuerySource src, long long n,
-                                                  float* __restrict__ out, int out_mode) {
-  const int r = threadIdx.x;
-  const long long qi = (long long)blockIdx.x * TILE_M + r;
-  const float4* x = reinterpret_cast<const float4*>(R) + (size_t)blockIdx.x * (N / 4) * TILE_M + r;
-  const int n4 = N / 4;
-  float dot = 0.f;
-  if (gam) {
-    const float shift = __ldg(&x[0]).x;
-    float s = 0.f, ss = 0.f;
-#pragma unroll 8
-    for (int c = 0; c < n4; ++c) {
-      float4 v = __ldg(&x[(size_t)c * TILE_M]);
-      float a0 = v.x - shift, a1 = v.y - shift, a2 = v.z - shift, a3 = v.w - shift;
-      s += (a0 + a1) + (a2 + a3);
-      ss += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
-    }
-    const float ms = s / N, mean = shift + ms;
-    const float rstd = rsqrtf(fmaxf(ss / N - ms * ms, 0.f) + 1e-5f);
-#pragma unroll 8
-    for (int c = 0; c < n4; ++c) {
-      float4 v = __ldg(&x[(size_t)c * TILE_M]);
-      const float4 gg = __ldg(reinterpret_cast<const float4*>(gam) + c), bb = __ldg(reinterpret_cast<const float4*>(bet) + c);
-      const float4 ww = __ldg(reinterpret_cast<const float4*>(wout) + c);
-      dot += ((v.x - mean) * rstd * gg.x + bb.x) * ww.x + ((v.y - mean) * rstd * gg.y + bb.y) * ww.y +
-             ((v.z - mean) * rstd * gg.z + bb.z) * ww.z + ((v.w - mean) * rstd * gg.w + bb.w) * ww.w;
-    }
-  } else {
-#pragma unroll 8
-    for (int c = 0; c < n4; ++c) {
-      float4 v = __ldg(&x[(size_t)c * TILE_M]);
-      const float4 ww = __ldg(reinterpret_cast<const float4*>(wout) + c);
-      dot += v.x * ww.x + v.y * ww.y + v.z * ww.z + v.w * ww.w;
-    }
-  }
-  if (qi >= n) return;
-  long long oi = qi;
-  if (out_mode == 1) { oi = src.index[qi]; if (oi < 0) return; }
-  out[oi] = dot + __ldg(bout);
-}
-
 // logits from the per-row partial statistics of x2 written by the last GEMM's epilogue:
 // [ln_post](x2) . wout + bout = rstd * (dot(x2, gamma*wout) - mean * C1) + C2   (C1 = sum gamma*wout, C2 = beta.wout + bout)
 __global__ void __launch_bounds__(128) k_head_final(const float* __restrict__ st, int S, int n_p, int ln_post, const float* __restrict__ c12,
@@ -643,6 +616,11 @@ __global__ void __launch_bounds__(256) k_head_consts(const float* __restrict__ g
   __syncthreads();
   for (int o = 128; o; o >>= 1) { if (threadIdx.x < o) { r1[threadIdx.x] += r1[threadIdx.x + o]; r2[threadIdx.x] += r2[threadIdx.x + o]; } __syncthreads(); }
   if (threadIdx.x == 0) { c12[0] = r1[0]; c12[1] = r2[0] + bout[0]; }
+}
+
+__global__ void k_add_vec(const float* __restrict__ a, const float* __restrict__ b, int n, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (a ? a[i] : 0.f) + (b ? b[i] : 0.f);
 }
 
 // LayerNorm fold: Wf[j][k] = gamma[k] * W[j][k];  cs[j] = sum_k fp16(Wf[j][k]);  bb[j] = sum_k beta[k] W[j][k] + bias[j]
@@ -786,10 +764,12 @@ int launch_gemm(hy3d_ctx* ctx, const GemmTC& g, int fam) {
     k_finish_stats<<<(unsigned)ceil_div64(rows, 256), 256, 0, ctx->stream>>>(g.st_in, g.st_slots, g.st_np, g.ln_eps, rows, ctx->ln_mr.as<float2>());
     ctx->launches++;
   }
-  CUtensorMap tmA, tmB;
-  if (int rc = make_rows_map(ctx, &tmA, g.A, (uint64_t)g.Mb * g.KB * 128)) return rc;
+  CUtensorMap tmA, tmA2, tmB;
+  const int kb1 = g.KB1 ? g.KB1 : g.KB;
+  if (int rc = make_rows_map(ctx, &tmA, g.A, (uint64_t)g.Mb * kb1 * 128)) return rc;
+  if (int rc = make_rows_map(ctx, &tmA2, g.A2 ? g.A2 : g.A, (uint64_t)g.Mb * (g.A2 ? g.KB - kb1 : kb1) * 128)) return rc;
   if (int rc = make_rows_map(ctx, &tmB, g.B, (uint64_t)g.Nb * g.KB * 256)) return rc;
-  k_gemm_tc<EPI><<<grid, GEMM_THREADS, GEMM_SMEM, ctx->stream>>>(gd, tmA, tmB);
+  k_gemm_tc<EPI><<<grid, GEMM_THREADS, GEMM_SMEM, ctx->stream>>>(gd, tmA, tmA2, tmB);
   HY3D_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -865,7 +845,8 @@ int hy3d_tc_prepare_weights(hy3d_ctx* ctx) {
   const size_t W = w.W, R = w.R;
   const size_t n_qp = W * 192, n_cq = W * W, n_cp = W * W, n_fc = R * W * W, n_mp = R * W * W, n_cq3 = 3 * W * W;
   const size_t n_ckv3 = 2 * W * 3 * W, n_lp3 = w.has_latents_proj ? W * 3 * (size_t)w.LW : 0;
-  HY3D_CUDA(ctx, w.tc.reserve((n_qp + n_cq + n_cp + n_fc + n_mp + n_cq3 + n_ckv3 + n_lp3) * 2));
+  const size_t n_cpx = W * (W + 192);                               // [c_proj | query_proj split] concatenated along K
+  HY3D_CUDA(ctx, w.tc.reserve((n_qp + n_cq + n_cp + n_fc + n_mp + n_cq3 + n_ckv3 + n_lp3 + n_cpx) * 2));
   __half* base = w.tc.as<__half>();
   __half* p_qp = base; __half* p_cq = p_qp + n_qp; __half* p_cp = p_cq + n_cq; __half* p_fc = p_cp + n_cp; __half* p_mp = p_fc + n_fc;
   auto build = [&](const float* src, int N, int K, int ldw, int mode, __half* dst) -> int {
@@ -875,7 +856,7 @@ int hy3d_tc_prepare_weights(hy3d_ctx* ctx) {
     return 0;
   };
   // ln_1 folded into c_q, ln_3 into c_fc, ln_post into the head (see GemmTC)
-  HY3D_CUDA(ctx, w.fold.reserve((W + W + R * W + R * W + W + 64 + 4 * W) * sizeof(float)));
+  HY3D_CUDA(ctx, w.fold.reserve((W + W + R * W + R * W + W + 64 + 4 * W + W) * sizeof(float)));
   HY3D_CUDA(ctx, ctx->ws[10].reserve(R * W * W * sizeof(float)));
   float* fb = w.fold.as<float>();
   float* cs_q = fb; float* bb_q = cs_q + W; float* cs_fc = bb_q + W; float* bb_fc = cs_fc + R * W; float* dotw = bb_fc + R * W; float* c12 = dotw + W;
@@ -914,6 +895,23 @@ int hy3d_tc_prepare_weights(hy3d_ctx* ctx) {
     if (w.has_latents_proj)
       if (int rc = build(w.lp_w, (int)W, (int)(3 * w.LW), (int)w.LW, 2, p_lp3)) return rc;
     w.t_ckv3 = p_ckv3; w.t_lp3 = w.has_latents_proj ? p_lp3 : nullptr; w.cs_kv = cs_kv; w.bb_kv = bb_kv;
+  }
+  // x1 = x0 + c_proj(attn) + b  as ONE GEMM over K = W + 192: [attn | e_hi | e_lo | e_hi] [W_o | W_qp,hi | W_qp,hi | W_qp,lo]^T
+  // + (b_o + b_qp) — the fp32 x0 never travels through HBM.  Tile images are concatenated per 256-row block.
+  {
+    __half* p_cpx = p_cq3 + n_cq3 + n_ckv3 + n_lp3;
+    const size_t kb_o = W / 64, kb_x = kb_o + 3;
+    for (size_t nb = 0; nb < W / BN; ++nb) {
+      uint8_t* dst = reinterpret_cast<uint8_t*>(p_cpx) + nb * kb_x * BTILE_BYTES;
+      HY3D_CUDA(ctx, cudaMemcpyAsync(dst, reinterpret_cast<const uint8_t*>(p_cp) + nb * kb_o * BTILE_BYTES, kb_o * BTILE_BYTES,
+                                     cudaMemcpyDeviceToDevice, ctx->stream));
+      HY3D_CUDA(ctx, cudaMemcpyAsync(dst + kb_o * BTILE_BYTES, reinterpret_cast<const uint8_t*>(p_qp) + nb * 3 * BTILE_BYTES, 3 * BTILE_BYTES,
+                                     cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    float* b_cpx = c12 + 64 + 4 * W;
+    k_add_vec<<<(unsigned)((W + 255) / 256), 256, 0, ctx->stream>>>(w.cproj_b, w.qp_b, (int)W, b_cpx);
+    HY3D_LAUNCH_CHECK(ctx);
+    w.t_cpx = p_cpx; w.b_cpx = b_cpx;
   }
   return 0;
 }
@@ -1027,17 +1025,21 @@ static int decode_tc_impl(hy3d_ctx* ctx, const QuerySource& src_in, long long n,
     return hy3d_fail(ctx, HY3D_ERR_UNSUPPORTED, "tcgen05 path needs head_dim 64 and widths that are multiples of 256");
   const int W = w.W, H = w.H, R = w.R;
   const int S = ST_PER_TILE * (W / BN);                         // statistic slots per row (one per 64 output columns)
-  const long long CH = 131072;                                 // points per chunk (1024 tiles)
+  const long long CH = ctx->chunk_points;                      // points per chunk (multiple of 256: whole CTA-pair tiles)
   const long long chmax = n < CH ? (n + 127) / 128 * 128 : CH;
   HY3D_CUDA(ctx, ctx->ws[2].reserve((size_t)chmax * W * 4));          // R32 residual stream
   HY3D_CUDA(ctx, ctx->ws[3].reserve((size_t)chmax * W * 2));          // T16 a (embed / raw x0 / attn out)
   HY3D_CUDA(ctx, ctx->ws[4].reserve((size_t)chmax * W * 2));          // T16 q, then raw x1
   HY3D_CUDA(ctx, ctx->ws[5].reserve((size_t)chmax * W * R * 2));      // T16 h
   HY3D_CUDA(ctx, ctx->ws[9].reserve((size_t)chmax * S * 7 * 4));      // row statistics: x0 (2), x1 (2), x2 (3) per slot
+  HY3D_CUDA(ctx, ctx->ws[6].reserve((size_t)chmax * 192 * 2));        // T16 Fourier features [hi | lo | hi] (kept for the fused c_proj)
+  // x0 stays out of HBM unless the per-stage activations are being retained for diagnostics
+  const bool fuse_x0 = !ctx->debug_retain && !(ctx->xbits & 0x80);
   float* x = ctx->ws[2].as<float>();
   uint8_t* ta = ctx->ws[3].as<uint8_t>();
   uint8_t* tq = ctx->ws[4].as<uint8_t>();
   uint8_t* th = ctx->ws[5].as<uint8_t>();
+  uint8_t* te = ctx->ws[6].as<uint8_t>();
   float* st1 = ctx->ws[9].as<float>();
   float* st3 = st1 + (size_t)chmax * S * 2;
   float* stp = st3 + (size_t)chmax * S * 2;
@@ -1051,12 +1053,12 @@ static int decode_tc_impl(hy3d_ctx* ctx, const QuerySource& src_in, long long n,
     else if (src.mode == 1) src.first += p0;
     else src.index += p0;
     HY3D_PROF(ctx, FAM_EMBED);
-    k_embed_tc<<<Pb, 128, 0, ctx->stream>>>(src, P, w.F, pi_mul, ta);
+    k_embed_tc<<<Pb, 128, 0, ctx->stream>>>(src, P, w.F, pi_mul, te);
     HY3D_LAUNCH_CHECK(ctx);
     GemmTC g{};
-    // x0 = query_proj(e): fp32 residual + raw fp16 copy + row statistics for the folded ln_1
-    g.Mb = Pb; g.A = ta; g.B = reinterpret_cast<const uint8_t*>(w.t_qp); g.KB = 3; g.N = W; g.Nb = W / BN; g.bias = w.qp_b;
-    g.Rout = x; g.Tcopy = tq; g.st_out = st1; g.st_k = 2;
+    // x0 = query_proj(e): raw fp16 copy + row statistics for the folded ln_1 (+ the fp32 residual when not fused)
+    g.Mb = Pb; g.A = te; g.B = reinterpret_cast<const uint8_t*>(w.t_qp); g.KB = 3; g.N = W; g.Nb = W / BN; g.bias = w.qp_b;
+    g.Rout = fuse_x0 ? nullptr : x; g.Tcopy = tq; g.st_out = st1; g.st_k = 2;
     if (int rc = launch_gemm<EPI_X0>(ctx, g, FAM_GEMM_QPROJ)) return rc;
     if (int rc = hy3d_debug_keep(ctx, 0, x, (size_t)Pp * W * 4, 1, Pp, W)) return rc;
     if (int rc = hy3d_debug_keep(ctx, 1, tq, (size_t)Pp * W * 2, 2, Pp, W)) return rc;
@@ -1081,8 +1083,12 @@ static int decode_tc_impl(hy3d_ctx* ctx, const QuerySource& src_in, long long n,
     if (int rc = hy3d_debug_keep(ctx, 3, tq, (size_t)Pp * W * 2, 2, Pp, W)) return rc;
     // x1 = x0 + c_proj(attn): fp32 residual in place + raw fp16 copy + statistics for the folded ln_3
     g = GemmTC{}; g.Mb = Pb;
-    g.A = tq; g.B = reinterpret_cast<const uint8_t*>(w.t_cproj); g.KB = W / 64; g.N = W; g.Nb = W / BN; g.bias = w.cproj_b;
-    g.Rin = x; g.Rout = x; g.Tcopy = ta; g.st_out = st3; g.st_k = 2;
+    if (fuse_x0) {       // [attn | e] [W_o | W_qp]^T + (b_o + b_qp): K-concatenated, no fp32 x0 in memory
+      g.A = tq; g.KB1 = W / 64; g.A2 = te; g.KB = W / 64 + 3; g.B = reinterpret_cast<const uint8_t*>(w.t_cpx); g.bias = w.b_cpx;
+    } else {
+      g.A = tq; g.KB = W / 64; g.B = reinterpret_cast<const uint8_t*>(w.t_cproj); g.bias = w.cproj_b; g.Rin = x;
+    }
+    g.N = W; g.Nb = W / BN; g.Rout = x; g.Tcopy = ta; g.st_out = st3; g.st_k = 2;
     if (int rc = launch_gemm<EPI_RES>(ctx, g, FAM_GEMM_CPROJ)) return rc;
     if (int rc = hy3d_debug_keep(ctx, 4, x, (size_t)Pp * W * 4, 1, Pp, W)) return rc;
     if (int rc = hy3d_debug_keep(ctx, 5, ta, (size_t)Pp * W * 2, 2, Pp, W)) return rc;

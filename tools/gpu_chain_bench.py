@@ -72,6 +72,9 @@ for bits in [int(b) for b in args.bits.split(",")]:
                 res["families"][f] = d
         if bits & 8:        # SM clock during each GEMM family = cycles of CTA 0 / device time
             tm = ctx.debug_timers()
+            n = max(tm[19], 1)  # all GEMM launches pooled: cycles per pair-tile of the leader MMA warp / one epilogue warp
+            res["gemm_clk_per_tile"] = {"mma_wait_tempty": round(tm[16] / n), "mma_wait_full": round(tm[17] / n), "mma_issue": round(tm[18] / n),
+                                        "epi_wait_tfull": round(tm[20] / n), "epi_work": round(tm[21] / n)}
             fam_of = {0: "gemm_query_proj", 1: "gemm_c_q", 3: "gemm_c_fc"}
             for epi, fam in fam_of.items():
                 if fam in res["families"] and tm[24 + epi]:
