@@ -203,18 +203,19 @@ k_gemm_tc(GemmTC g, const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int p = cid; p < npairs; p += ncl) {
       int mb = 2 * (p / g.Nb) + rank; const int nb = p % g.Nb;
       if (mb >= g.Mb) mb = g.Mb - 1;   // odd tile count: the idle half still feeds its share of B (its results are dropped)
-      // operands as rows of 128 bytes (tensor maps tmA / tmB): A tile (mb, kb) = rows [(mb KB + kb) 128, +128),
+      // operands through the tensor maps tmA / tmA2 / tmB: A tile (mb, kb) = tile index mb KB + kb,
       // this CTA's half of B tile (nb, kb) = rows [(nb KB + kb) 256 + 128 rank, +128)
       const int kb1 = g.KB1 ? g.KB1 : g.KB;
-      const int arow = mb * kb1 * 128, a2row = mb * (g.KB - kb1) * 128, brow = nb * g.KB * 256 + rank * 128;
+      // tensor-map rows are 2 KB: a 16 KB tile = 8 rows
+      const int arow = mb * kb1 * 8, a2row = mb * (g.KB - kb1) * 8, brow = nb * g.KB * 16 + rank * 8;
       for (int kb = 0; kb < g.KB; ++kb) {
         mbar_wait(EMPTY(s), ph ^ 1);
         if (elect_one()) {
           // both CTAs' copies complete on the LEADER's FULL(s) (64 KB per stage): no software relay on the critical path
           if (rank == 0) mbar_arrive_expect_tx(FULL(s), 4 * TILE_BYTES);
-          if (kb < kb1) tma2d_g2s_pair(smem_u32(sA + s * TILE_BYTES), &tmA, 0, arow + kb * 128, FULL(s));
-          else tma2d_g2s_pair(smem_u32(sA + s * TILE_BYTES), &tmA2, 0, a2row + (kb - kb1) * 128, FULL(s));
-          tma2d_g2s_pair(smem_u32(sB + s * TILE_BYTES), &tmB, 0, brow + kb * 256, FULL(s));
+          if (kb < kb1) tma2d_g2s_pair(smem_u32(sA + s * TILE_BYTES), &tmA, 0, arow + kb * 8, FULL(s));
+          else tma2d_g2s_pair(smem_u32(sA + s * TILE_BYTES), &tmA2, 0, a2row + (kb - kb1) * 8, FULL(s));
+          tma2d_g2s_pair(smem_u32(sB + s * TILE_BYTES), &tmB, 0, brow + kb * 16, FULL(s));
         }
         __syncwarp();
         if (++s == GEMM_STAGES) { s = 0; ph ^= 1; }
@@ -707,8 +708,8 @@ __global__ void k_build_kv(const float* __restrict__ k32, const float* __restric
   }
 }
 
-// Tensor map over an operand image viewed as rows of 128 bytes (every UMMA tile is 128 or 256 such rows, already
-// swizzled in memory): box = 128 rows x 128 bytes = one 16 KB tile, no hardware swizzle.  cuTensorMapEncodeTiled comes
+// Tensor map over an operand image viewed as a plain 2-D byte array (every UMMA tile is a contiguous 16 KB block, already
+// swizzled in memory): box = one 16 KB tile, no hardware swizzle.  cuTensorMapEncodeTiled comes
 // from the driver through the runtime (no link-time libcuda dependency).
 int make_rows_map(hy3d_ctx* ctx, CUtensorMap* m, const void* base, uint64_t rows) {
   typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -721,11 +722,13 @@ int make_rows_map(hy3d_ctx* ctx, CUtensorMap* m, const void* base, uint64_t rows
     if (!fn || q != cudaDriverEntryPointSuccess) return hy3d_fail(ctx, HY3D_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
     encode = reinterpret_cast<encode_fn>(fn);
   }
-  const cuuint64_t dims[2] = {128, rows};
-  const cuuint64_t strides[1] = {128};
-  const cuuint32_t box[2] = {128, 128};
+  // `rows` counts 128-byte rows; the map itself uses rows of 256 x 8 bytes (2 KB): a 16 KB tile = box of 8 such rows, so the
+  // TMA unit walks 8 long rows per tile instead of 128 short ones
+  const cuuint64_t dims[2] = {256, rows / 16};
+  const cuuint64_t strides[1] = {2048};
+  const cuuint32_t box[2] = {256, 8};
   const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = encode(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  const CUresult r = encode(m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return hy3d_fail(ctx, HY3D_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
   return 0;
