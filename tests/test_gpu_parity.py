@@ -190,7 +190,9 @@ def test_decoder_matches_reference_golden(tag, gold, dev, ctx):
 
 
 def test_decoder_ragged_sizes_and_chunks(dev, ctx):
-    """Empty, 1, non-multiples of the 128-row tile, and more than one 131072-point chunk."""
+    """Empty, 1, non-multiples of the 128-row tile (odd tile counts leave one CTA of a pair idle), and more than one
+    262144-point chunk."""
+    CH = 262144
     cfg = W.MINI
     sd = W.synthetic_state_dict(cfg, seed=0, with_transformer=False)
     gd = hy3dgeo.GeoDecoder(W.geo_decoder_state(sd), cfg)
@@ -199,10 +201,10 @@ def test_decoder_ragged_sizes_and_chunks(dev, ctx):
     c.prepare_kv(lat[0])
     gsd, fr = W.geo_decoder_state(sd), W.fourier_frequencies(cfg)
     assert c.decode_points(torch.empty(0, 3, device=dev)).numel() == 0
-    pts = (torch.rand(131072 + 129, 3, generator=torch.Generator().manual_seed(4)) * 2 - 1) * 1.01
+    pts = (torch.rand(CH + 129, 3, generator=torch.Generator().manual_seed(4)) * 2 - 1) * 1.01
     out = c.decode_points(pts.to(dev)).cpu()
     c.check_watchdog()
-    for sl in (slice(0, 1), slice(127, 130), slice(131071, 131072 + 129)):
+    for sl in (slice(0, 1), slice(127, 130), slice(CH - 1, CH + 129)):
         ref = OD.geo_decoder_forward(gsd, pts[None, sl], lat.cpu(), fr, cfg.dec_heads)[0, :, 0]
         assert float((out[sl] - ref).abs().max()) < LOGIT_TOL
     one = c.decode_points(pts[:1].to(dev)).cpu()
