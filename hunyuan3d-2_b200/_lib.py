@@ -90,6 +90,10 @@ SYMBOLS = {
                                 C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_float)]),
     "hy3d_mc_emit": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                c_f32p, c_i32p]),
+    "hy3d_mc_count_slab": (C.c_int, [C.c_void_p, c_f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float,
+                                     C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_float)]),
+    "hy3d_mc_emit_slab": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                    C.c_int32, C.c_int64, c_f32p, c_i32p]),
     "hy3d_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "hy3d_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "hy3d_debug_watchdog": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
@@ -431,6 +435,22 @@ class GeoContext:
         m = (C.c_double * 3)(*[float(v) for v in mul])
         a = (C.c_double * 3)(*[float(v) for v in add])
         self._check(self.lib.hy3d_mc_emit(self.h, d, m, a, _ptr(verts), _ptr(faces)), "hy3d_mc_emit")
+
+    def mc_count_slab(self, grid: torch.Tensor, own_planes: int, level: float):
+        """grid = owned planes followed by the next slab's halo planes; counts of the owned part (see hy3dgeo.h)."""
+        self.sync_stream()
+        nv, nf = C.c_int64(), C.c_int64()
+        mm = (C.c_float * 3)()
+        self._check(self.lib.hy3d_mc_count_slab(self.h, _ptr(grid), grid.shape[0], grid.shape[1], grid.shape[2], int(own_planes),
+                                                float(level), C.byref(nv), C.byref(nf), mm), "hy3d_mc_count_slab")
+        return nv.value, nf.value, (mm[0], mm[1], bool(mm[2]))
+
+    def mc_emit_slab(self, div, mul, add, plane0: int, id_base: int, verts: torch.Tensor, faces: torch.Tensor):
+        self.sync_stream()
+        d = (C.c_double * 3)(*[float(v) for v in div])
+        m = (C.c_double * 3)(*[float(v) for v in mul])
+        a = (C.c_double * 3)(*[float(v) for v in add])
+        self._check(self.lib.hy3d_mc_emit_slab(self.h, d, m, a, int(plane0), int(id_base), _ptr(verts), _ptr(faces)), "hy3d_mc_emit_slab")
 
     def mc_cases(self, grid: torch.Tensor, level: float) -> torch.Tensor:
         self.sync_stream()

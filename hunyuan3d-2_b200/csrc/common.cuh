@@ -89,6 +89,7 @@ struct McState {
   bool counted = false;
   const float* grid = nullptr;
   int n0 = 0, n1 = 0, n2 = 0, words = 0;
+  int own_planes = 0;                 // slab mode: planes [0, own_planes) are owned, the rest is the next slab's halo
   float level = 0.f;
   long long nV = 0, nF = 0;
   DevBuf bits, rowcnt, rowoff, stats;

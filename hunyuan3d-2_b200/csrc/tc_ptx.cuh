@@ -68,33 +68,6 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
-// non-suspending variant: mbarrier.test_wait never parks the thread, so the waiter reacts within a few cycles of the
-// phase flip (try_wait may park it for a system-dependent time slice)
-__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
-  uint32_t spins = 0;
-  while (!mbar_test_wait(bar, parity)) {
-    if ((++spins & 0xfffu) != 0) continue;
-    const uint32_t limit = (*(volatile int*)&hy3d_wd[0]) ? (1u << 12) : (1u << 26);
-    if (spins >= limit) {
-      if (atomicExch(&hy3d_wd[0], 1) == 0) {
-        hy3d_wd[1] = (int)blockIdx.x; hy3d_wd[2] = (int)threadIdx.x; hy3d_wd[3] = (int)bar; hy3d_wd[4] = (int)parity;
-      }
-      return;
-    }
-  }
-}
-
 // ---- async proxy ---------------------------------------------------------------------------
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -126,15 +99,6 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// global -> shared 1-D bulk copy delivered to the same CTA-relative offset in every CTA of `cta_mask`; each
-// destination CTA's mbarrier (same offset) receives the complete_tx
-__device__ __forceinline__ void bulk_g2s_multicast(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar, uint16_t cta_mask) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst_smem),
-      "l"(src), "r"(bytes), "r"(bar), "h"(cta_mask)
-      : "memory");
-}
-
 // arrive (release, cluster scope) on the mbarrier at the same offset in CTA `cta` of the cluster
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
   asm volatile(
@@ -143,39 +107,6 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
       "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar), "r"(cta)
       : "memory");
 }
-// wait with cluster-scope acquire: pairs with mbar_arrive_remote from the peer CTA
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-  uint32_t spins = 0;
-  for (;;) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (ok) return;
-#if HY3D_TC_WATCHDOG
-    if ((++spins & 0xffu) != 0) continue;
-    const uint32_t limit = (*(volatile int*)&hy3d_wd[0]) ? (1u << 8) : (1u << 22);
-    if (spins >= limit) {
-      if (atomicExch(&hy3d_wd[0], 1) == 0) {
-        hy3d_wd[1] = (int)blockIdx.x; hy3d_wd[2] = (int)threadIdx.x; hy3d_wd[3] = (int)bar; hy3d_wd[4] = (int)parity;
-      }
-      return;
-    }
-#endif
-  }
-}
-
-// shared::cluster address of the same offset in CTA `cta`
-__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t cta) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
-  return r;
-}
-
 // ---- tcgen05 -------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
@@ -210,13 +141,6 @@ __device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uin
 // arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-// the same arrival delivered to the mbarrier at this offset in every CTA of `cta_mask`
-__device__ __forceinline__ void mma_commit_multicast(uint32_t bar, uint16_t cta_mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-               "h"(cta_mask)
-               : "memory");
 }
 
 // ---- CTA-pair (cta_group::2) forms: one MMA spans two SMs (M = 256: 128 rows per CTA; each CTA supplies its A rows
@@ -308,12 +232,6 @@ __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
-}
-
-__device__ __forceinline__ __half2 ex2_h2(__half2 x) {
-  uint32_t xi = *reinterpret_cast<uint32_t*>(&x), yi;
-  asm("ex2.approx.f16x2 %0, %1;" : "=r"(yi) : "r"(xi));
-  return *reinterpret_cast<__half2*>(&yi);
 }
 
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {

@@ -9,8 +9,10 @@ Exchange steps (the only collectives):
   * refined-level values   -> all ranks (all_gather of equal padded value ranges);
   * latents are replicated by the caller (each rank receives the same ``latents``; use
     ``broadcast_latents`` when only rank 0 holds them).
-Marching cubes then runs on rank 0 over the assembled grid: at 385^3 the grid is 228 MB
-(~0.3 ms over NVLink) and the extraction itself ~0.1 ms, far below one decoder tile of work.
+Marching cubes either runs on rank 0 over the assembled grid (at 385^3 the grid is 228 MB, ~0.3 ms
+over NVLink) or stays sharded (``extract_mesh_sharded``): every rank keeps its slab, receives a
+two-plane halo from its upper neighbour, extracts the part of the mesh it owns with globally
+consistent vertex ids, and only the mesh pieces travel to rank 0 (BASELINE config 5).
 
 The communication helpers take any decode callables, so the host logic is testable on CPU with
 gloo and a fake field (tests/test_parallel_gloo.py).
@@ -92,6 +94,82 @@ def decode_dense_sharded(decode_range: Callable[[int, int, torch.Tensor], None],
     return grid.view(n0, n1, n2) if rank == 0 else None
 
 
+MC_HALO = 2      # planes of the next slab a rank needs (hy3dgeo.h: hy3d_mc_count_slab)
+
+
+def exchange_halo(local: torch.Tensor, halo: int = MC_HALO, group=None) -> torch.Tensor:
+    """``local`` = this rank's planes [p, n1, n2] of an axis-0 partition (every slab at least ``halo`` planes deep).
+    Returns them followed by the first ``halo`` planes of the next rank's slab (nothing on the last rank): one
+    batched send/recv between neighbours, N^2 * halo * 4 bytes per rank."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if world == 1:
+        return local
+    if local.shape[0] < halo:
+        raise ValueError(f"slab of {local.shape[0]} planes is thinner than the {halo}-plane halo")
+    ops, recv = [], None
+    if rank > 0:
+        ops.append(dist.P2POp(dist.isend, local[:halo].contiguous(), rank - 1, group))
+    if rank < world - 1:
+        recv = torch.empty((halo,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        ops.append(dist.P2POp(dist.irecv, recv, rank + 1, group))
+    for q in dist.batch_isend_irecv(ops):
+        q.wait()
+    return local if recv is None else torch.cat([local, recv], 0)
+
+
+def extract_mesh_sharded(local: torch.Tensor, plane0: int, count_slab: Callable, emit_slab: Callable, mc_level: float,
+                         group=None, dst: int = 0):
+    """Marching cubes over a grid that stays partitioned along axis 0.
+
+    local      : this rank's planes [plane0, plane0 + p) of the grid, [p, n1, n2]
+    count_slab : (slab_with_halo, own_planes) -> (nV, nF, (vmin, vmax, has_nan))     (MCSurfaceExtractor.count_slab)
+    emit_slab  : (nV, nF, plane0, id_base) -> (verts [nV, 3] float32, faces [nF, 3] int32), face ids global
+    Returns (verts, faces) on ``dst`` — exactly the mesh of the whole grid: rank pieces are contiguous ranges of the
+    global lexicographic vertex / face order — and None elsewhere.  Raises the errors of
+    ``skimage.measure.marching_cubes`` (level outside the data range, no surface) on every rank alike."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    slab = exchange_halo(local, MC_HALO, group)
+    nv, nf, (vmin, vmax, has_nan) = count_slab(slab, local.shape[0])
+    inf = float("inf")
+    mine = torch.tensor([nv, nf, vmin if vmin == vmin else inf, vmax if vmax == vmax else -inf, float(has_nan)],
+                        dtype=torch.float64, device=local.device)
+    allst = torch.empty((world, 5), dtype=torch.float64, device=local.device)
+    dist.all_gather(list(allst.unbind(0)), mine, group=group)
+    allst = allst.cpu()
+    nvs, nfs = [int(v) for v in allst[:, 0]], [int(v) for v in allst[:, 1]]
+    gmin, gmax, any_nan = float(allst[:, 2].min()), float(allst[:, 3].max()), bool(allst[:, 4].max() > 0)
+    if not any_nan and (mc_level < gmin or mc_level > gmax):
+        raise ValueError("Surface level must be within volume data range.")
+    if sum(nfs) == 0:
+        raise RuntimeError("No surface found at the given iso value.")
+    verts, faces = emit_slab(nv, nf, plane0, sum(nvs[:rank]))
+    # mesh pieces -> dst: one batched group of point-to-point copies (sizes differ per rank)
+    ops, V, F = [], None, None
+    if rank == dst:
+        V = torch.empty((sum(nvs), 3), dtype=torch.float32, device=local.device)
+        F = torch.empty((sum(nfs), 3), dtype=torch.int32, device=local.device)
+        vo, fo = 0, 0
+        for r in range(world):
+            if r == rank:
+                V[vo: vo + nvs[r]] = verts
+                F[fo: fo + nfs[r]] = faces
+            else:
+                if nvs[r]:
+                    ops.append(dist.P2POp(dist.irecv, V[vo: vo + nvs[r]], r, group))
+                if nfs[r]:
+                    ops.append(dist.P2POp(dist.irecv, F[fo: fo + nfs[r]], r, group))
+            vo += nvs[r]; fo += nfs[r]
+    else:
+        if nv:
+            ops.append(dist.P2POp(dist.isend, verts.contiguous(), dst, group))
+        if nf:
+            ops.append(dist.P2POp(dist.isend, faces.contiguous(), dst, group))
+    if ops:
+        for q in dist.batch_isend_irecv(ops):
+            q.wait()
+    return (V, F) if rank == dst else None
+
+
 def decode_list_sharded(decode_values: Callable[[torch.Tensor], torch.Tensor], index: torch.Tensor, group=None) -> torch.Tensor:
     """``decode_values(index_slice) -> logits`` for an ordered index list known identically on all
     ranks; each rank evaluates its contiguous share, the values are all-gathered."""
@@ -168,6 +246,36 @@ class ShardedHierarchicalVolumeDecoding:
             outs.append(grid)
             self.last_stats.append({"levels": levels, "queries": queries})
         return torch.stack(outs, 0).to(latents.dtype)
+
+
+def vanilla_latents2mesh_sharded(latents, geo_decoder, surface_extractor=None, group=None, bounds=1.01, mc_level=0.0,
+                                 octree_resolution=None, **kwargs):
+    """VanillaVolumeDecoder + MCSurfaceExtractor with the grid left in place (BASELINE config 5): every rank decodes
+    its slab, marching cubes runs per slab behind a two-plane halo exchange, rank 0 receives the mesh pieces.
+    Returns ``list[Latent2MeshOutput | None]`` on rank 0 (the reference's per-item error convention) and None elsewhere."""
+    from .surface_extractors import Latent2MeshOutput, MCSurfaceExtractor
+    ext = surface_extractor if surface_extractor is not None else MCSurfaceExtractor()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    ctx = bind(latents, geo_decoder)
+    axes = axis_tables(bounds, octree_resolution)
+    N = int(octree_resolution) + 1
+    x0, x1 = slab_planes(N, rank, world)
+    outs = []
+    for b in range(latents.shape[0]):
+        ctx.prepare_kv(latents[b])
+        local = torch.empty((x1 - x0, N, N), dtype=torch.float32, device=latents.device)
+        ctx.decode_dense(axes, x0 * N * N, (x1 - x0) * N * N, local)
+        try:
+            res = extract_mesh_sharded(
+                local, x0, lambda slab, own: ext.count_slab(slab, own, mc_level),
+                lambda nv, nf, p0, base: ext.emit_slab(nv, nf, p0, base, bounds=bounds, octree_resolution=octree_resolution),
+                mc_level, group)
+            outs.append(None if res is None else Latent2MeshOutput(mesh_v=res[0].cpu().numpy(), mesh_f=res[1].cpu().numpy()))
+        except (ValueError, RuntimeError):
+            import traceback
+            traceback.print_exc()
+            outs.append(None)
+    return outs if rank == 0 else None
 
 
 def latents2mesh_data_parallel(vae, latents, group=None, dst: int = 0, **kwargs):

@@ -82,6 +82,25 @@ class MCSurfaceExtractor(SurfaceExtractor):
                                        octree_resolution=octree_resolution, **kwargs)
         return verts.cpu().numpy(), faces.cpu().numpy()
 
+    # ---- slab forms (hy3dgeo.parallel.extract_mesh_sharded): a grid partitioned along axis 0 ------------------------
+    def count_slab(self, slab: torch.Tensor, own_planes: int, mc_level: float):
+        """slab = this rank's planes followed by the halo (first planes of the next slab).  -> (nV, nF, (min, max, nan))
+        of the owned part."""
+        if not isinstance(slab, torch.Tensor) or not slab.is_cuda:
+            raise RuntimeError("MCSurfaceExtractor needs a CUDA tensor (hy3dgeo has no CPU path)")
+        self._slab = slab.detach().to(torch.float32).contiguous()
+        return get_context(slab.device).mc_count_slab(self._slab, own_planes, mc_level)
+
+    def emit_slab(self, nv: int, nf: int, plane0: int, id_base: int, *, bounds, octree_resolution):
+        """Vertices / faces of the slab counted last; face ids are global (id_base = vertices of all earlier slabs)."""
+        grid_size, bbox_min, bbox_size = self._compute_box_stat(bounds, octree_resolution)
+        dev = self._slab.device
+        verts = torch.empty((nv, 3), dtype=torch.float32, device=dev)
+        faces = torch.empty((nf, 3), dtype=torch.int32, device=dev)
+        if nv or nf:
+            get_context(dev).mc_emit_slab(grid_size, bbox_size, bbox_min, plane0, id_base, verts, faces)
+        return verts, faces
+
 
 class DMCSurfaceExtractor(SurfaceExtractor):
     """reference :79-94 wraps ``diso.DiffDMC``; out of scope for this path (SURVEY §2 row 2,

@@ -177,6 +177,19 @@ int hy3d_mc_count(hy3d_ctx* ctx, const float* d_grid, int32_t n0, int32_t n1, in
  * d_verts: fp32 [V,3]; d_faces: int32 [F,3]. */
 int hy3d_mc_emit(hy3d_ctx* ctx, const double h_div[3], const double h_mul[3], const double h_add[3],
                  float* d_verts, int32_t* d_faces);
+/* Slab forms for grids partitioned along axis 0 across GPUs (no reference counterpart: the reference is single-device;
+ * SURVEY §8e).  d_grid holds planes [plane0, plane0 + n0) of the whole grid: the first `own_planes` are OWNED by this
+ * slab, the rest (two planes, fewer at the end of the grid) are the next slab's first planes, kept as a halo.  Counted
+ * and emitted: the vertices on edges starting at owned voxels and the triangles of cubes based at owned planes.  Vertex
+ * and face orders are the global lexicographic ones, so the meshes of consecutive slabs concatenate into exactly the
+ * mesh hy3d_mc_count / hy3d_mc_emit produce for the whole grid when each slab passes
+ *   id_base = number of vertices owned by all earlier slabs
+ * (faces of the last owned plane reference vertices of the first halo plane: their ids continue past this slab's own
+ * count, which is why the halo is two planes deep — the ids depend on that plane's axis-0 edges too). */
+int hy3d_mc_count_slab(hy3d_ctx* ctx, const float* d_grid, int32_t n0, int32_t n1, int32_t n2, int32_t own_planes, float level,
+                       int64_t* h_num_verts, int64_t* h_num_faces, float h_minmax[3]);
+int hy3d_mc_emit_slab(hy3d_ctx* ctx, const double h_div[3], const double h_mul[3], const double h_add[3], int32_t plane0,
+                      int64_t id_base, float* d_verts, int32_t* d_faces);
 /* Table-independent classification for parity tests: 8-bit case per cube, [n0-1,n1-1,n2-1]. */
 int hy3d_mc_cases(hy3d_ctx* ctx, const float* d_grid, int32_t n0, int32_t n1, int32_t n2, float level,
                   uint8_t* d_cases);

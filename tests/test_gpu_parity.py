@@ -111,6 +111,30 @@ def test_mc_extractor_contract(dev):
     assert f16.shape[0] > 0
 
 
+@pytest.mark.parametrize("shape,parts", [((17, 9, 33), 2), ((24, 12, 40), 3), ((31, 17, 65), 8)])
+def test_mc_slabs_concatenate_to_whole_mesh(dev, ctx, shape, parts):
+    """Slab forms (hy3d_mc_count_slab / hy3d_mc_emit_slab, the multi-GPU partition of SURVEY §8e): the meshes of
+    consecutive axis-0 slabs, each seeing a two-plane halo of the next one, concatenate bit-exactly into the mesh of
+    the whole grid (vertex bits, face ids) — random field with NaNs, all ranks emulated on one device."""
+    from hy3dgeo.parallel import MC_HALO, slab_planes
+    g = torch.randn(shape, generator=torch.Generator().manual_seed(11))
+    g[3, 2, 5] = float("nan")
+    g = g.to(dev)
+    ext = MCSurfaceExtractor()
+    kw = dict(bounds=1.01, octree_resolution=shape[0] - 1)
+    v_ref, f_ref = ext.run_device(g, mc_level=0.1, **kw)
+    vs, fs, base = [], [], 0
+    for r in range(parts):
+        x0, x1 = slab_planes(shape[0], r, parts)
+        slab = g[x0:min(x1 + MC_HALO, shape[0])].contiguous()
+        nv, nf, _ = ext.count_slab(slab, x1 - x0, 0.1)
+        v, f = ext.emit_slab(nv, nf, x0, base, **kw)
+        vs.append(v); fs.append(f); base += nv
+    v, f = torch.cat(vs), torch.cat(fs)
+    assert v.shape == v_ref.shape and f.shape == f_ref.shape
+    assert torch.equal(v.view(torch.int32), v_ref.view(torch.int32)) and torch.equal(f, f_ref)
+
+
 @pytest.mark.parametrize("n", [257, 385])
 def test_mc_full_size_properties(ctx, n):
     """BASELINE grid sizes: V == number of sign-change grid edges, closed genus-0 surface F == 2V-4,

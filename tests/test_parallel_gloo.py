@@ -10,7 +10,7 @@ import torch.multiprocessing as mp
 
 import hy3dgeo  # noqa: F401
 from hy3dgeo import parallel as P
-from oracle import volume as OV
+from oracle import mc as OM, volume as OV
 
 
 def field(p):
@@ -53,6 +53,43 @@ def _worker(rank, world, port, q):
                 return [("mesh", int(lat[0, 0, 0]), kw["octree_resolution"])]
         outs = P.latents2mesh_data_parallel(FakeVAE(), torch.arange(5.).view(5, 1, 1), None, 0, octree_resolution=9)
         ok = ok and (outs == [("mesh", b, 9) for b in range(5)] if rank == 0 else outs is None)
+        # sharded marching cubes (config 5): halo exchange, global vertex ids, mesh gather — oracle MC as the slab extractor
+        x0, x1 = P.slab_planes(N, rank, world)
+        full_np = ref.astype(np.float32)
+        state = {}
+
+        def count_slab(slab, own):
+            sub = slab.numpy()
+            try:
+                v, f, _, _ = OM.marching_cubes(sub, 0.0)
+            except (ValueError, RuntimeError):
+                state.update(v=np.zeros((0, 3), np.float32), f=np.zeros((0, 3), np.int32))
+                return 0, 0, (float(sub.min()), float(sub.max()), False)
+            owned = int((np.floor(v[:, 0]) < own).sum())              # vertices are in lexicographic voxel order: a prefix
+            if own + 1 < sub.shape[0]:                                # triangles of the cubes based at owned planes
+                try:
+                    vt, ft, _, _ = OM.marching_cubes(sub[:own + 1], 0.0)
+                    lut = {tuple(p): i for i, p in enumerate(map(tuple, v))}
+                    ft = np.array([[lut[tuple(vt[i])] for i in tri] for tri in ft], np.int32).reshape(-1, 3)
+                except (ValueError, RuntimeError):
+                    ft = np.zeros((0, 3), np.int32)
+            else:
+                ft = f
+            state.update(v=v[:owned], f=ft)
+            return owned, len(ft), (float(sub.min()), float(sub.max()), False)
+
+        def emit_slab(nv, nf, plane0, id_base):
+            v = state["v"].copy(); v[:, 0] += plane0
+            return torch.from_numpy(v), torch.from_numpy(state["f"] + np.int32(id_base))
+        mesh = P.extract_mesh_sharded(torch.from_numpy(full_np[x0:x1].copy()), x0, count_slab, emit_slab, 0.0, None, 0)
+        if rank == 0:
+            v_ref, f_ref, _, _ = OM.marching_cubes(full_np, 0.0)
+            # faces exact; vertices to 1 ulp (this CPU stand-in adds the plane offset after the float32 rounding — the CUDA
+            # kernels interpolate in the global index frame and are bit-exact, tests/test_gpu_parity.py)
+            ok = ok and np.array_equal(mesh[1].numpy(), f_ref) and mesh[0].shape == v_ref.shape and \
+                bool(np.abs(mesh[0].numpy() - v_ref).max() < 2e-6)
+        else:
+            ok = ok and mesh is None
         lat = P.broadcast_latents(torch.arange(6.).view(2, 3) if rank == 0 else None, (2, 3), "cpu")
         ok = ok and bool((lat == torch.arange(6.).view(2, 3)).all())
         q.put((rank, bool(ok)))
