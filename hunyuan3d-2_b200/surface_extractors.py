@@ -14,6 +14,17 @@ import torch
 from ._lib import get_context
 
 
+def _to_host(*tensors):
+    """Device tensors -> numpy arrays through pinned host memory (torch's caching host allocator): both copies are
+    queued on the current stream and one synchronisation follows; the arrays alias the pinned tensors that own them.
+    (Pageable ``.cpu()`` copies run at a few GB/s — ~35 ms for a 100 MB mesh — pinned ones at PCIe speed.)"""
+    host = [torch.empty(t.shape, dtype=t.dtype, device="cpu", pin_memory=True) for t in tensors]
+    for h, t in zip(host, tensors):
+        h.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(tensors[0].device).synchronize()
+    return tuple(h.numpy() for h in host)
+
+
 class Latent2MeshOutput:
     """reference surface_extractors.py:22-26."""
 
@@ -41,7 +52,7 @@ class SurfaceExtractor:
         for i in range(grid_logits.shape[0]):
             try:
                 vertices, faces = self.run(grid_logits[i], **kwargs)
-                vertices = vertices.astype(np.float32)
+                vertices = vertices.astype(np.float32, copy=False)
                 faces = np.ascontiguousarray(faces)
                 outputs.append(Latent2MeshOutput(mesh_v=vertices, mesh_f=faces))
             except Exception:
@@ -80,7 +91,7 @@ class MCSurfaceExtractor(SurfaceExtractor):
     def run(self, grid_logit, *, mc_level, bounds, octree_resolution, **kwargs):
         verts, faces = self.run_device(grid_logit, mc_level=mc_level, bounds=bounds,
                                        octree_resolution=octree_resolution, **kwargs)
-        return verts.cpu().numpy(), faces.cpu().numpy()
+        return _to_host(verts, faces)
 
     # ---- slab forms (hy3dgeo.parallel.extract_mesh_sharded): a grid partitioned along axis 0 ------------------------
     def count_slab(self, slab: torch.Tensor, own_planes: int, mc_level: float):
