@@ -184,8 +184,10 @@ __device__ __forceinline__ float exp2_poly(float x) {
 }
 template <int kPoly>
 __device__ __forceinline__ bool exp_on_fma(int i) {
-  constexpr unsigned kMask = kPoly == 0 ? 0x00u : kPoly == 1 ? 0x10u : kPoly == 2 ? 0x22u : kPoly == 3 ? 0x52u : kPoly == 4 ? 0xAAu : 0xEEu;
-  return ((kMask >> (i & 7)) & 1u) != 0;
+  // 16-element patterns: kPoly 1 = 2/16, 5 = 3/16, 2 = 4/16, 3 = 6/16, 4 = 8/16
+  constexpr unsigned kMask = kPoly == 0 ? 0x0000u : kPoly == 1 ? 0x1010u : kPoly == 5 ? 0x0842u : kPoly == 2 ? 0x2222u : kPoly == 3 ? 0x5252u
+                           : kPoly == 4 ? 0xAAAAu : 0xEEEEu;
+  return ((kMask >> (i & 15)) & 1u) != 0;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -125,7 +125,7 @@ struct hy3d_ctx {
   void* pinned = nullptr;             // small pinned host buffer for read-backs
   Prof prof;
   // diagnostics: per-stage activations of the last decoded chunk (hy3d_debug_retain / hy3d_debug_fetch)
-  int attn_poly = 1;                  // of every 8 attention exponentials, how many run on the FMA pipe (HY3D_ATTN_POLY: 0..4; bounded-score kernel)
+  int attn_poly = 5;                  // share of the attention exponentials on the FMA pipe (HY3D_ATTN_POLY: 0 none, 1 = 2/16, 5 = 3/16, 2 = 4/16, 3 = 6/16, 4 = 8/16; bounded-score kernel)
   int debug_retain = 0;
   long long chunk_points = 262144;    // decoder chunk (HY3D_CHUNK; 131072 measured 1 % slower, 32768 7 % slower): activations of one chunk are what the stages hand over through L2 / HBM
   int xbits = 0;                      // HY3D_DBG: experiment bits for tools/gpu_chain_bench.py (results are garbage when set)

@@ -728,8 +728,12 @@ int make_rows_map(hy3d_ctx* ctx, CUtensorMap* m, const void* base, uint64_t rows
   const cuuint64_t strides[1] = {2048};
   const cuuint32_t box[2] = {256, 8};
   const cuuint32_t estr[2] = {1, 1};
+  static int promo = -1;                       // HY3D_L2PROMO = 0 none, 1 64 B, 2 128 B, 3 256 B (default)
+  if (promo < 0) { const char* e = getenv("HY3D_L2PROMO"); promo = e ? atoi(e) : 3; }
+  const CUtensorMapL2promotion pr = promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                  : promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
   const CUresult r = encode(m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                            CU_TENSOR_MAP_SWIZZLE_NONE, pr, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return hy3d_fail(ctx, HY3D_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
   return 0;
 }
@@ -804,6 +808,7 @@ int launch_attn(hy3d_ctx* ctx, AttnTC a, bool fast, int fam) {
         case 2: rc = launch_attn_kernel(ctx, k_attn_fast<2, false>, a, ATT_FAST_THREADS); break;
         case 3: rc = launch_attn_kernel(ctx, k_attn_fast<3, false>, a, ATT_FAST_THREADS); break;
         case 4: rc = launch_attn_kernel(ctx, k_attn_fast<4, false>, a, ATT_FAST_THREADS); break;
+        case 5: rc = launch_attn_kernel(ctx, k_attn_fast<5, false>, a, ATT_FAST_THREADS); break;
         default: rc = launch_attn_kernel(ctx, k_attn_fast<0, false>, a, ATT_FAST_THREADS); break;
       }
     }

@@ -216,8 +216,9 @@ int hy3d_debug_retain(hy3d_ctx* ctx, int enable);
  * (1 GEMM epilogue, 2 GEMM MMAs, 4 GEMM epilogue stores) so that their cost can be measured by difference — results
  * are garbage while those are set; 0x20 forces the online-softmax attention kernel, 0x40 runs the instrumented
  * bounded-score attention kernel (hy3d_debug_timers), 0x10000 the CUDA-core K/V projection (results stay valid);
- * `attn_poly` = how many of every 8 attention exponentials run on the FMA pipe (0, 2, 3, 4, 6).
- * Defaults (0, 0) are the product configuration. */
+ * `attn_poly` = share of the attention exponentials evaluated on the FMA pipe (0 none, 1 = 2/16, 5 = 3/16, 2 = 4/16,
+ * 3 = 6/16, 4 = 8/16).
+ * Defaults (0, 5) are the product configuration. */
 int hy3d_debug_experiment(hy3d_ctx* ctx, int bits, int attn_poly);
 /* Phase clocks accumulated by the instrumented attention kernel (experiment bit 0x40), returned and cleared:
  * per head stream a (0, 1) h_out[8a + i] = SM cycles one softmax thread of CTA 0 spent in phase i
