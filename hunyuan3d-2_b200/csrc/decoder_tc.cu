@@ -38,6 +38,7 @@ constexpr int TILE_M = 128;
 constexpr int TILE_BYTES = 16384;          // 128 x 64 fp16
 constexpr int BN = 256;                    // GEMM N tile
 constexpr int BTILE_BYTES = BN * 128;      // 256 x 64 fp16
+constexpr int GEMM_CL = 2;                // CTAs per cluster: 2 = one MMA pair (product); 4 = two pairs sharing the B tile by multicast TMA (measured 5-10 % slower: only 33 such clusters = 132 of 148 SMs are co-resident)
 constexpr int GEMM_STAGES = 5;            // 32 KB per stage and CTA: A tile + half of the B tile (+ 64 KB of output staging)
 constexpr int GEMM_THREADS = 640;          // warp0 producer, warp1 mma, warp2 tmem, warp3 idle, warps 4..19 epilogue
 constexpr int ST_PER_TILE = 4;             // row-statistic slots per 256-column tile (one per epilogue warp column quarter)
@@ -159,13 +160,12 @@ __device__ __forceinline__ void store_t16_split(uint8_t* t0, uint8_t* t1, uint8_
 // of 48 KB: with single-SM MMAs the TMA fills plus the operand reads already take ~190 B/clk of shared-memory
 // bandwidth and every epilogue load/store slowed the tensor pipe (full kernel 30 % slower than max(MMA-only,
 // epilogue-only)).  Barrier protocol (s = smem stage, acc = accumulator buffer):
-//   FULL(s)   local TMA bytes of this CTA's stage            -> leader MMA warp; peer's warp 1 relays it to the leader's PFULL(s)
-//   PFULL(s)  (leader) the peer's stage s is full             -> leader MMA warp
+//   FULL(s)   (leader) TMA bytes of BOTH CTAs' stage s, 64 KB -> leader MMA warp
 //   EMPTY(s)  multicast tcgen05.commit of the leader          -> both producers
 //   TFULL(a)  multicast tcgen05.commit of the leader          -> both CTAs' epilogue warps
 //   TEMPTY(a) (leader) 16 local + 16 remote epilogue arrivals -> leader MMA warp
 template <int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __cluster_dims__(GEMM_CL, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 k_gemm_tc(GemmTC g, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -176,15 +176,14 @@ k_gemm_tc(GemmTC g, const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t bar0 = smem_u32(bars);
   auto FULL = [&](int s) { return bar0 + 8u * s; };
   auto EMPTY = [&](int s) { return bar0 + 8u * (GEMM_STAGES + s); };
-  auto PFULL = [&](int s) { return bar0 + 8u * (2 * GEMM_STAGES + s); };
-  auto TFULL = [&](int a) { return bar0 + 8u * (3 * GEMM_STAGES + a); };
-  auto TEMPTY = [&](int a) { return bar0 + 8u * (3 * GEMM_STAGES + 2 + a); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * GEMM_STAGES + 4);
+  auto TFULL = [&](int a) { return bar0 + 8u * (2 * GEMM_STAGES + a); };
+  auto TEMPTY = [&](int a) { return bar0 + 8u * (2 * GEMM_STAGES + 2 + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * GEMM_STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long clk0 = (g.dbg & 8) ? clock64() : 0;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < GEMM_STAGES; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); mbar_init(PFULL(s), 1); }
+    for (int s = 0; s < GEMM_STAGES; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), GEMM_CL / 2); }
     for (int a = 0; a < 2; ++a) { mbar_init(TFULL(a), 1); mbar_init(TEMPTY(a), 32); }
     fence_barrier_init();
   }
@@ -194,20 +193,25 @@ k_gemm_tc(GemmTC g, const __grid_constant__ CUtensorMap tmA, const __grid_consta
   fence_after_sync();
   const uint32_t tmem = *tmem_slot;
   // work item p of cluster c: tile pair (m-blocks 2 (p / Nb) + {0, 1}, n-block p % Nb); this CTA holds m-block + rank
-  const int rank = (int)cluster_ctarank();
-  const int npairs = ((g.Mb + 1) / 2) * g.Nb;
-  const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+  // (GEMM_CL = 4: two pairs with the same n-block; each CTA fetches a QUARTER of the B tile and multicasts it to the CTA of the
+  //  other pair that holds the same B half — 24 KB instead of 32 KB of L2 -> SM traffic per CTA and k-block)
+  const int crank = (int)cluster_ctarank();
+  const int rank = crank & 1, pair = crank >> 1;          // position inside the MMA pair, pair inside the cluster
+  const int npairs = ((g.Mb + GEMM_CL - 1) / GEMM_CL) * g.Nb;
+  const int cid = blockIdx.x / GEMM_CL, ncl = gridDim.x / GEMM_CL;
+  const uint16_t mask_all = (uint16_t)((1u << GEMM_CL) - 1), mask_pair = (uint16_t)(3u << (2 * pair));
 
   if (warp == 0) {
     int s = 0; uint32_t ph = 0;
     for (int p = cid; p < npairs; p += ncl) {
-      int mb = 2 * (p / g.Nb) + rank; const int nb = p % g.Nb;
-      if (mb >= g.Mb) mb = g.Mb - 1;   // odd tile count: the idle half still feeds its share of B (its results are dropped)
+      int mb = GEMM_CL * (p / g.Nb) + crank; const int nb = p % g.Nb;
+      if (mb >= g.Mb) mb = g.Mb - 1;   // ragged tile count: the idle CTAs still feed their share of B (their results are dropped)
       // operands through the tensor maps tmA / tmA2 / tmB: A tile (mb, kb) = tile index mb KB + kb,
       // this CTA's half of B tile (nb, kb) = rows [(nb KB + kb) 256 + 128 rank, +128)
       const int kb1 = g.KB1 ? g.KB1 : g.KB;
       // tensor-map rows are 2 KB: a 16 KB tile = 8 rows
-      const int arow = mb * kb1 * 8, a2row = mb * (g.KB - kb1) * 8, brow = nb * g.KB * 16 + rank * 8;
+      const int arow = mb * kb1 * 8, a2row = mb * (g.KB - kb1) * 8;
+      const int brow = nb * g.KB * 16 + rank * 8 + (GEMM_CL == 4 ? pair * 4 : 0);
       for (int kb = 0; kb < g.KB; ++kb) {
         mbar_wait(EMPTY(s), ph ^ 1);
         if (elect_one()) {
@@ -215,7 +219,11 @@ k_gemm_tc(GemmTC g, const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (rank == 0) mbar_arrive_expect_tx(FULL(s), 4 * TILE_BYTES);
           if (kb < kb1) tma2d_g2s_pair(smem_u32(sA + s * TILE_BYTES), &tmA, 0, arow + kb * 8, FULL(s));
           else tma2d_g2s_pair(smem_u32(sA + s * TILE_BYTES), &tmA2, 0, a2row + (kb - kb1) * 8, FULL(s));
-          tma2d_g2s_pair(smem_u32(sB + s * TILE_BYTES), &tmB, 0, brow + kb * 16, FULL(s));
+          if (GEMM_CL == 4)
+            tma2d_g2s_pair_multicast(smem_u32(sB + s * TILE_BYTES + pair * (TILE_BYTES / 2)), &tmB, 0, brow + kb * 16, FULL(s),
+                                     (uint16_t)((1u << crank) | (1u << (crank ^ 2))));
+          else
+            tma2d_g2s_pair(smem_u32(sB + s * TILE_BYTES), &tmB, 0, brow + kb * 16, FULL(s));
         }
         __syncwarp();
         if (++s == GEMM_STAGES) { s = 0; ph ^= 1; }
@@ -247,8 +255,8 @@ k_gemm_tc(GemmTC g, const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (!(g.dbg & 2))
 #pragma unroll
             for (int k = 0; k < 4; ++k) mma2_f16_ss(d, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
-          mma2_commit_multicast(EMPTY(s), (uint16_t)3);
-          if (kb == g.KB - 1) mma2_commit_multicast(TFULL(acc), (uint16_t)3);
+          mma2_commit_multicast(EMPTY(s), mask_all);
+          if (kb == g.KB - 1) mma2_commit_multicast(TFULL(acc), mask_pair);
         }
         __syncwarp();
         if (tmr) { const long long t_ = clock64(); tw[2] += t_ - tw0; tw0 = t_; }
@@ -266,7 +274,7 @@ k_gemm_tc(GemmTC g, const __grid_constant__ CUtensorMap tmA, const __grid_consta
     long long te0 = 0, te[2] = {0, 0};              // (experiment bit 8) cycles: wait TFULL, work
     const bool tmr = (g.dbg & 8) && blockIdx.x == 0 && warp == 4;
     for (int p = cid; p < npairs; p += ncl, ++it) {
-      const int mb = 2 * (p / g.Nb) + rank, nb = p % g.Nb;
+      const int mb = GEMM_CL * (p / g.Nb) + crank, nb = p % g.Nb;
       const int acc = it & 1;
       const uint32_t aph = (it >> 1) & 1;
       if (tmr) { const long long t_ = clock64(); if (it) te[1] += t_ - te0; te0 = t_; }
@@ -275,7 +283,7 @@ k_gemm_tc(GemmTC g, const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (tmr) { const long long t_ = clock64(); te[0] += t_ - te0; te0 = t_; }
       if ((g.dbg & 1) || mb >= g.Mb) {
         fence_before_sync(); __syncwarp();
-        if (lane == 0) { if (rank == 0) mbar_arrive(TEMPTY(acc)); else mbar_arrive_remote(TEMPTY(acc), 0); }
+        if (lane == 0) { if (rank == 0) mbar_arrive(TEMPTY(acc)); else mbar_arrive_remote(TEMPTY(acc), crank & ~1); }
         continue;
       }
       const uint32_t tcol = tmem + acc * BN + cq * 64 + ((uint32_t)(q * 32) << 16);
@@ -490,7 +498,7 @@ k_gemm_tc(GemmTC g, const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       fence_before_sync();
       __syncwarp();
-      if (lane == 0) { if (rank == 0) mbar_arrive(TEMPTY(acc)); else mbar_arrive_remote(TEMPTY(acc), 0); }
+      if (lane == 0) { if (rank == 0) mbar_arrive(TEMPTY(acc)); else mbar_arrive_remote(TEMPTY(acc), crank & ~1); }
     }
     if (tmr && lane == 0) { te[1] += clock64() - te0; atomicAdd(&hy3d_tm[20], (unsigned long long)te[0]); atomicAdd(&hy3d_tm[21], (unsigned long long)te[1]); }
   }
@@ -711,7 +719,7 @@ __global__ void k_build_kv(const float* __restrict__ k32, const float* __restric
 // Tensor map over an operand image viewed as a plain 2-D byte array (every UMMA tile is a contiguous 16 KB block, already
 // swizzled in memory): box = one 16 KB tile, no hardware swizzle.  cuTensorMapEncodeTiled comes
 // from the driver through the runtime (no link-time libcuda dependency).
-int make_rows_map(hy3d_ctx* ctx, CUtensorMap* m, const void* base, uint64_t rows) {
+int make_rows_map(hy3d_ctx* ctx, CUtensorMap* m, const void* base, uint64_t rows, int box_rows = 8) {
   typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
   static encode_fn encode = nullptr;
@@ -726,7 +734,7 @@ int make_rows_map(hy3d_ctx* ctx, CUtensorMap* m, const void* base, uint64_t rows
   // TMA unit walks 8 long rows per tile instead of 128 short ones
   const cuuint64_t dims[2] = {256, rows / 16};
   const cuuint64_t strides[1] = {2048};
-  const cuuint32_t box[2] = {256, 8};
+  const cuuint32_t box[2] = {256, (cuuint32_t)box_rows};     // 8 rows of 2 KB = one 16 KB tile (4 = half of it)
   const cuuint32_t estr[2] = {1, 1};
   static int promo = -1;                       // HY3D_L2PROMO = 0 none, 1 64 B, 2 128 B, 3 256 B (default)
   if (promo < 0) { const char* e = getenv("HY3D_L2PROMO"); promo = e ? atoi(e) : 3; }
@@ -754,14 +762,14 @@ int launch_gemm(hy3d_ctx* ctx, const GemmTC& g, int fam) {
   static int max_clusters = 0;                                     // co-resident 2-CTA clusters (persistent grid)
   if (max_clusters == 0) {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(ctx->num_sms / 2 * 2); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = GEMM_SMEM;
+    cfg.gridDim = dim3(ctx->num_sms / GEMM_CL * GEMM_CL); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = GEMM_SMEM;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, k_gemm_tc<EPI>, &cfg) != cudaSuccess || n <= 0) { n = ctx->num_sms / 2; (void)cudaGetLastError(); }
-    max_clusters = n < ctx->num_sms / 2 ? n : ctx->num_sms / 2;
-    if (getenv("HY3D_VERBOSE")) fprintf(stderr, "[hy3dgeo] k_gemm_tc<%d>: %d co-resident 2-CTA clusters\n", EPI, max_clusters);
+    if (cudaOccupancyMaxActiveClusters(&n, k_gemm_tc<EPI>, &cfg) != cudaSuccess || n <= 0) { n = ctx->num_sms / GEMM_CL; (void)cudaGetLastError(); }
+    max_clusters = n < ctx->num_sms / GEMM_CL ? n : ctx->num_sms / GEMM_CL;
+    if (getenv("HY3D_VERBOSE")) fprintf(stderr, "[hy3dgeo] k_gemm_tc<%d>: %d co-resident %d-CTA clusters\n", EPI, max_clusters, GEMM_CL);
   }
-  const int pairs = ((g.Mb + 1) / 2) * g.Nb;                       // one tile pair per cluster iteration
-  const int grid = 2 * (pairs < max_clusters ? pairs : max_clusters);
+  const int pairs = ((g.Mb + GEMM_CL - 1) / GEMM_CL) * g.Nb;        // one group of GEMM_CL vertically adjacent tiles per cluster iteration
+  const int grid = GEMM_CL * (pairs < max_clusters ? pairs : max_clusters);
   HY3D_PROF(ctx, fam);
   GemmTC gd = g; gd.dbg = ctx->xbits & 15;
   if (g.st_in) {
@@ -775,7 +783,7 @@ int launch_gemm(hy3d_ctx* ctx, const GemmTC& g, int fam) {
   const int kb1 = g.KB1 ? g.KB1 : g.KB;
   if (int rc = make_rows_map(ctx, &tmA, g.A, (uint64_t)g.Mb * kb1 * 128)) return rc;
   if (int rc = make_rows_map(ctx, &tmA2, g.A2 ? g.A2 : g.A, (uint64_t)g.Mb * (g.A2 ? g.KB - kb1 : kb1) * 128)) return rc;
-  if (int rc = make_rows_map(ctx, &tmB, g.B, (uint64_t)g.Nb * g.KB * 256)) return rc;
+  if (int rc = make_rows_map(ctx, &tmB, g.B, (uint64_t)g.Nb * g.KB * 256, GEMM_CL == 4 ? 4 : 8)) return rc;
   k_gemm_tc<EPI><<<grid, GEMM_THREADS, GEMM_SMEM, ctx->stream>>>(gd, tmA, tmA2, tmB);
   HY3D_LAUNCH_CHECK(ctx);
   return 0;

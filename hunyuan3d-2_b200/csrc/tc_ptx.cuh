@@ -178,6 +178,15 @@ __device__ __forceinline__ void tma2d_g2s_pair(uint32_t dst_smem, const void* tm
                : "memory");
 }
 
+// the same, delivered to every CTA of `cta_mask` (same CTA-relative offset); each destination's pair leader gets the complete_tx
+__device__ __forceinline__ void tma2d_g2s_pair_multicast(uint32_t dst_smem, const void* tmap, int c0, int c1, uint32_t bar, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(
+          dst_smem),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(bar & 0xFEFFFFFFu), "h"(cta_mask)
+      : "memory");
+}
+
 // instruction descriptor, .kind::f16: D=f32, A=B=f16, both K-major, dense
 __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
   return (1u << 4)                    // c_format = F32
