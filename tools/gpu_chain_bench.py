@@ -20,7 +20,7 @@ ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--tag", default="")
 ap.add_argument("--no-pre", action="store_true", help="skip the transformer / K/V timings (short kernel sequence for ncu)")
 ap.add_argument("--bits", default="0", help="comma list of experiment bit sets")
-ap.add_argument("--poly", default="0", help="comma list of attn_poly values")
+ap.add_argument("--poly", default="5", help="comma list of attn_poly values (5 = product default)")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 cfg = W.FULL if args.model == "full" else W.MINI
@@ -86,4 +86,4 @@ for bits in [int(b) for b in args.bits.split(",")]:
             tm = ctx.debug_timers()
             res["softmax_clk_per_tile"] = [[round(tm[8 * a + i] / max(tm[8 * a + 7], 1)) for i in range(6)] for a in range(2)]
         print(json.dumps(res), flush=True)
-ctx.debug_experiment(0, 0)
+ctx.debug_experiment(0, 5)
