@@ -34,32 +34,33 @@ class Latent2MeshOutput:
 
 
 class SurfaceExtractor:
+    """Plugin base (reference surface_extractors.py:37-64): ``extractor(grid_logits, **kwargs)`` maps a batch of grids
+    to one ``Latent2MeshOutput`` per item; an item whose ``run`` raises becomes ``None`` (the traceback is printed,
+    nothing propagates) — the pipeline relies on that to skip failed samples."""
+
     def _compute_box_stat(self, bounds: Union[Tuple[float], List[float], float], octree_resolution: int):
-        """reference :38-45 (grid_size is res+1 per axis, whatever the grid's own size)."""
-        if isinstance(bounds, float):
-            bounds = [-bounds, -bounds, -bounds, bounds, bounds, bounds]
-        bbox_min, bbox_max = np.array(bounds[0:3]), np.array(bounds[3:6])
-        bbox_size = bbox_max - bbox_min
-        grid_size = [int(octree_resolution) + 1, int(octree_resolution) + 1, int(octree_resolution) + 1]
-        return grid_size, bbox_min, bbox_size
+        """(grid_size, bbox_min, bbox_size) of the vertex rescale ``v / grid_size * bbox_size + bbox_min``.  As in the
+        reference (:38-45) ``grid_size`` is ``octree_resolution + 1`` on every axis whatever the grid's own shape
+        (FlashVDM grids are 381^3 for resolution 384, and indices span 0..res)."""
+        b = [-bounds] * 3 + [bounds] * 3 if isinstance(bounds, float) else list(bounds)
+        lo, hi = np.array(b[:3]), np.array(b[3:6])
+        return [int(octree_resolution) + 1] * 3, lo, hi - lo
 
     def run(self, *args, **kwargs):
-        return NotImplementedError
+        return NotImplementedError            # sic: the reference returns (not raises) it, :47-48
 
     def __call__(self, grid_logits, **kwargs):
-        """reference :50-64."""
-        outputs = []
-        for i in range(grid_logits.shape[0]):
+        results = []
+        for item in range(grid_logits.shape[0]):
+            mesh = None
             try:
-                vertices, faces = self.run(grid_logits[i], **kwargs)
-                vertices = vertices.astype(np.float32, copy=False)
-                faces = np.ascontiguousarray(faces)
-                outputs.append(Latent2MeshOutput(mesh_v=vertices, mesh_f=faces))
+                verts, faces = self.run(grid_logits[item], **kwargs)
+                mesh = Latent2MeshOutput(mesh_v=verts.astype(np.float32, copy=False), mesh_f=np.ascontiguousarray(faces))
             except Exception:
                 import traceback
                 traceback.print_exc()
-                outputs.append(None)
-        return outputs
+            results.append(mesh)
+        return results
 
 
 class MCSurfaceExtractor(SurfaceExtractor):
