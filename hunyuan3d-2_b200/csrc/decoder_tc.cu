@@ -64,7 +64,7 @@ struct GemmTC {
   // (mean, M2) slots written by the producer's epilogue and are merged here (Chan et al.), deterministically.
   const float* st_in; int st_slots; int st_np; const float* cs; float ln_eps;
   const float2* ln_mr;   // per row (mean, rstd) merged from st_in by k_finish_stats (set by launch_gemm)
-  // statistics of the rows this GEMM produces (EPI_X0 / EPI_RES): slot nb*2+half <- (mean, M2[, dot with dotw])
+  // statistics of the rows this GEMM produces (EPI_X0 / EPI_RES): slot nb * 4 + column quarter <- (mean, M2[, dot with dotw]) of 64 columns
   float* st_out; int st_k; const float* dotw;
   uint8_t* Tcopy;        // fp16 T16 copy of the fp32 rows written to Rout (operand of the next GEMM)
   int split_out;         // Tcopy / Tout(GELU) written as [hi | lo | hi] (3 * N/64 k-blocks): operand of a 3-term split GEMM
