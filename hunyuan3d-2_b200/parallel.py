@@ -259,6 +259,8 @@ def vanilla_latents2mesh_sharded(latents, geo_decoder, surface_extractor=None, g
     ctx = bind(latents, geo_decoder)
     axes = axis_tables(bounds, octree_resolution)
     N = int(octree_resolution) + 1
+    if N < MC_HALO * world:            # decided identically on every rank: nobody is left waiting in the halo exchange
+        raise ValueError(f"{N} planes cannot be split into {world} slabs of at least {MC_HALO} planes")
     x0, x1 = slab_planes(N, rank, world)
     outs = []
     for b in range(latents.shape[0]):
