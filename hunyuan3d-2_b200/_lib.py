@@ -64,6 +64,7 @@ SYMBOLS = {
     "hy3d_last_error": (C.c_char_p, [C.c_void_p]),
     "hy3d_set_precision": (C.c_int, [C.c_void_p, C.c_int]),
     "hy3d_launch_count": (C.c_int64, [C.c_void_p]),
+    "hy3d_attention_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "hy3d_set_decoder_weights": (C.c_int, [C.c_void_p, C.POINTER(DecoderDesc)]),
     "hy3d_set_transformer_weights": (C.c_int, [C.c_void_p, C.POINTER(TransformerDesc)]),
     "hy3d_transformer_forward": (C.c_int, [C.c_void_p, c_f32p, C.c_int32, c_f32p]),
@@ -75,14 +76,14 @@ SYMBOLS = {
                                    C.POINTER(C.c_float), C.POINTER(C.c_float), c_f32p]),
     "hy3d_decode_list_values": (C.c_int, [C.c_void_p, c_i32p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                           C.POINTER(C.c_float), C.POINTER(C.c_float), c_f32p]),
-    "hy3d_scatter": (C.c_int, [C.c_void_p, c_i32p, c_f32p, C.c_int64, c_f32p]),
+    "hy3d_scatter": (C.c_int, [C.c_void_p, c_i32p, c_f32p, C.c_int64, C.c_int64, c_f32p]),
     "hy3d_flash_select": (C.c_int, [C.c_void_p, c_i32p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.POINTER(Coords),
                                     c_i32p, C.c_int32, C.c_int32, C.c_int32]),
     "hy3d_decode_flash": (C.c_int, [C.c_void_p, c_i32p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.POINTER(Coords),
                                     c_i32p, c_f32p]),
     "hy3d_flash_selection": (C.c_int, [C.c_void_p, c_i32p, C.c_int64]),
     "hy3d_flash_group_tokens": (C.c_int, [C.c_void_p, c_i32p, C.c_int32]),
-    "hy3d_refine_level": (C.c_int, [C.c_void_p, c_f32p, C.c_int32, C.c_float, C.c_int32, c_i32p, C.c_int64,
+    "hy3d_refine_level": (C.c_int, [C.c_void_p, c_f32p, C.c_int32, C.c_int32, C.c_float, C.c_int32, c_i32p, C.c_int64,
                                     C.POINTER(C.c_int64)]),
     "hy3d_fill": (C.c_int, [C.c_void_p, c_f32p, C.c_int64, C.c_float]),
     "hy3d_sentinel_to_nan": (C.c_int, [C.c_void_p, c_f32p, C.c_int64, C.c_float]),
@@ -178,6 +179,12 @@ class GeoContext:
     @property
     def launches(self) -> int:
         return int(self.lib.hy3d_launch_count(self.h))
+
+    def attention_info(self):
+        """(score bound, 'bounded-score' | 'online-softmax') of the decoder weights currently loaded."""
+        b, f = C.c_float(), C.c_int32()
+        self._check(self.lib.hy3d_attention_info(self.h, C.byref(b), C.byref(f)), "hy3d_attention_info")
+        return float(b.value), ("bounded-score" if f.value else "online-softmax")
 
     @staticmethod
     def _same_owner(ref, owner) -> bool:
@@ -357,9 +364,10 @@ class GeoContext:
                                                      _ptr(out)), "hy3d_decode_list_values")
         return out
 
-    def scatter(self, index: torch.Tensor, values: torch.Tensor, grid: torch.Tensor):
+    def scatter(self, index: torch.Tensor, values: torch.Tensor, grid: torch.Tensor, base: int = 0):
+        """grid.flat[index[q] - base] = values[q] (``base`` = flat offset of a slab's first plane in the whole grid)."""
         self.sync_stream()
-        self._check(self.lib.hy3d_scatter(self.h, _ptr(index.contiguous()), _ptr(values.contiguous()), index.numel(),
+        self._check(self.lib.hy3d_scatter(self.h, _ptr(index.contiguous()), _ptr(values.contiguous()), index.numel(), int(base),
                                           _ptr(grid)), "hy3d_scatter")
 
     # ---- FlashVDM ---------------------------------------------------------------------------
@@ -402,13 +410,15 @@ class GeoContext:
         return out
 
     # ---- octree -------------------------------------------------------------------------------
-    def refine_level(self, coarse: torch.Tensor, mc_level: float, last: bool, index: Optional[torch.Tensor]) -> int:
+    def refine_level(self, coarse: torch.Tensor, mc_level: float, last: bool, index: Optional[torch.Tensor],
+                     nf: Optional[int] = None) -> int:
+        """Active voxels of the fine grid [nf]^3 (default 2n-1; 2n when the level list came from an odd r // 2)."""
         self.sync_stream()
         n = coarse.shape[0]
         cnt = C.c_int64()
         cap = 0 if index is None else index.numel()
-        self._check(self.lib.hy3d_refine_level(self.h, _ptr(coarse), n, float(mc_level), int(last), _ptr(index), cap,
-                                               C.byref(cnt)), "hy3d_refine_level")
+        self._check(self.lib.hy3d_refine_level(self.h, _ptr(coarse), n, 2 * n - 1 if nf is None else int(nf), float(mc_level),
+                                               int(last), _ptr(index), cap, C.byref(cnt)), "hy3d_refine_level")
         return cnt.value
 
     def fill(self, grid: torch.Tensor, value: float):

@@ -151,6 +151,13 @@ int hy3d_set_precision(hy3d_ctx* ctx, int precision) {
 
 int64_t hy3d_launch_count(const hy3d_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+int hy3d_attention_info(const hy3d_ctx* ctx, float* h_score_bound, int32_t* h_bounded_kernel) {
+  if (!ctx || !h_score_bound || !h_bounded_kernel) return HY3D_ERR_ARG;
+  *h_score_bound = ctx->w.attn_bound;
+  *h_bounded_kernel = (ctx->w.attn_fast && !(ctx->xbits & 0x20)) ? 1 : 0;
+  return HY3D_OK;
+}
+
 int hy3d_set_decoder_weights(hy3d_ctx* ctx, const hy3d_decoder_desc* d) {
   if (!ctx || !d) return HY3D_ERR_ARG;
   HY3D_CUDA(ctx, cudaSetDevice(ctx->device));

@@ -158,12 +158,12 @@ __global__ void k_fill_f32(float* __restrict__ p, long long n, float v) {
   for (; t < n; t += stride) p[t] = v;
 }
 
-__global__ void k_scatter_f32(const int32_t* __restrict__ index, const float* __restrict__ vals, long long n,
+__global__ void k_scatter_f32(const int32_t* __restrict__ index, const float* __restrict__ vals, long long n, long long base,
                               float* __restrict__ grid) {
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
   int i = index[t];
-  if (i >= 0) grid[i] = vals[t];
+  if (i >= 0) grid[i - base] = vals[t];
 }
 
 __global__ void k_sentinel_nan(float* __restrict__ p, long long n, float sentinel) {
@@ -177,12 +177,14 @@ __global__ void k_sentinel_nan(float* __restrict__ p, long long n, float sentine
 
 extern "C" {
 
-int hy3d_refine_level(hy3d_ctx* ctx, const float* d_coarse, int32_t n, float mc_level, int32_t last_level, int32_t* d_index,
-                      int64_t cap, int64_t* h_count) {
+int hy3d_refine_level(hy3d_ctx* ctx, const float* d_coarse, int32_t n, int32_t nf, float mc_level, int32_t last_level,
+                      int32_t* d_index, int64_t cap, int64_t* h_count) {
   if (!ctx || !d_coarse || n < 2 || !h_count || cap < 0 || (cap > 0 && !d_index)) return HY3D_ERR_ARG;
+  // the fine grid is (r+1)^3 with r = 2 r_c or 2 r_c + 1 (levels are built with r // 2, volume_decoders.py:202-208):
+  // every up-sampled voxel 2c must exist (nf >= 2n - 1) and every fine voxel must have a coarse parent f >> 1 (nf <= 2n)
+  if (nf < 2 * n - 1 || nf > 2 * n) return hy3d_fail(ctx, HY3D_ERR_ARG, "fine grid %d^3 does not refine a %d^3 grid (need 2n-1 or 2n)", nf, n);
   HY3D_CUDA(ctx, cudaSetDevice(ctx->device));
   const long long nc = (long long)n * n * n;
-  const int nf = 2 * n - 1;
   const long long nfine = (long long)nf * nf * nf;
   if (nfine > 2147483647LL) return hy3d_fail(ctx, HY3D_ERR_UNSUPPORTED, "fine grid too large for int32 indices");
   const long long nwords = (nfine + 31) / 32;
@@ -233,17 +235,18 @@ int hy3d_fill(hy3d_ctx* ctx, float* d_grid, int64_t n, float value) {
   if (n == 0) return HY3D_OK;
   HY3D_CUDA(ctx, cudaSetDevice(ctx->device));
   int blocks = (int)(ceil_div64(n, 256) < (long long)ctx->num_sms * 16 ? ceil_div64(n, 256) : (long long)ctx->num_sms * 16);
+  HY3D_PROF(ctx, FAM_OCTREE);
   k_fill_f32<<<blocks, 256, 0, ctx->stream>>>(d_grid, n, value);
   HY3D_LAUNCH_CHECK(ctx);
   return HY3D_OK;
 }
 
-int hy3d_scatter(hy3d_ctx* ctx, const int32_t* d_index, const float* d_values, int64_t n, float* d_grid) {
-  if (!ctx || n < 0 || (n > 0 && (!d_index || !d_values || !d_grid))) return HY3D_ERR_ARG;
+int hy3d_scatter(hy3d_ctx* ctx, const int32_t* d_index, const float* d_values, int64_t n, int64_t base, float* d_grid) {
+  if (!ctx || n < 0 || base < 0 || (n > 0 && (!d_index || !d_values || !d_grid))) return HY3D_ERR_ARG;
   if (n == 0) return HY3D_OK;
   HY3D_CUDA(ctx, cudaSetDevice(ctx->device));
   HY3D_PROF(ctx, FAM_OCTREE);
-  k_scatter_f32<<<(unsigned)ceil_div64(n, 256), 256, 0, ctx->stream>>>(d_index, d_values, n, d_grid);
+  k_scatter_f32<<<(unsigned)ceil_div64(n, 256), 256, 0, ctx->stream>>>(d_index, d_values, n, base, d_grid);
   HY3D_LAUNCH_CHECK(ctx);
   return HY3D_OK;
 }
@@ -253,6 +256,7 @@ int hy3d_sentinel_to_nan(hy3d_ctx* ctx, float* d_grid, int64_t n, float sentinel
   if (n == 0) return HY3D_OK;
   HY3D_CUDA(ctx, cudaSetDevice(ctx->device));
   int blocks = (int)(ceil_div64(n, 256) < (long long)ctx->num_sms * 16 ? ceil_div64(n, 256) : (long long)ctx->num_sms * 16);
+  HY3D_PROF(ctx, FAM_OCTREE);
   k_sentinel_nan<<<blocks, 256, 0, ctx->stream>>>(d_grid, n, sentinel);
   HY3D_LAUNCH_CHECK(ctx);
   return HY3D_OK;

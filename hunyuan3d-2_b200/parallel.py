@@ -40,11 +40,54 @@ def list_range(n: int, rank: int, world: int) -> Tuple[int, int]:
     return slab_planes(n, rank, world)
 
 
+def _staged(t: torch.Tensor, group) -> bool:
+    """CUDA tensors under a gloo group (the 2-process tests that share one GPU) travel through host memory: gloo
+    moves device tensors for broadcast / all_reduce only.  Under NCCL nothing is staged."""
+    return t.is_cuda and dist.get_backend(group) == "gloo"
+
+
+def _peer(group, r: int) -> int:
+    """Global rank of group rank ``r``: P2POp / send / recv / broadcast name their peers by GLOBAL rank even when a
+    sub-group is passed."""
+    return r if group is None else dist.get_global_rank(group, r)
+
+
+def _run_p2p(sends, recvs, group):
+    """One batched group of point-to-point copies.  sends / recvs: lists of (tensor, group_rank); recv tensors may be
+    views (slices of a larger buffer) — they are filled in place."""
+    if not sends and not recvs:
+        return
+    ops, fix = [], []
+    for t, r in sends:
+        t = t.contiguous()
+        ops.append(dist.P2POp(dist.isend, t.cpu() if _staged(t, group) else t, _peer(group, r), group))
+    for t, r in recvs:
+        if _staged(t, group) or not t.is_contiguous():
+            buf = torch.empty(t.shape, dtype=t.dtype, device="cpu" if _staged(t, group) else t.device)
+            fix.append((t, buf))
+            ops.append(dist.P2POp(dist.irecv, buf, _peer(group, r), group))
+        else:
+            ops.append(dist.P2POp(dist.irecv, t, _peer(group, r), group))
+    for q in dist.batch_isend_irecv(ops):
+        q.wait()
+    for t, buf in fix:
+        t.copy_(buf)
+
+
+def agree(ok: bool, device, group=None) -> bool:
+    """True iff ``ok`` on every rank (one tiny all_reduce): lets all ranks leave a collective sequence together when
+    one of them failed, instead of the healthy ones blocking in the next exchange."""
+    flag = torch.tensor([0 if ok else 1], dtype=torch.int32, device="cpu" if dist.get_backend(group) == "gloo" else device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+    return int(flag.item()) == 0
+
+
 def broadcast_latents(latents: Optional[torch.Tensor], shape, device, group=None, src: int = 0) -> torch.Tensor:
+    """``src`` is a group rank."""
     if latents is None:
         latents = torch.empty(shape, dtype=torch.float32, device=device)
     latents = latents.contiguous()
-    dist.broadcast(latents, src=src, group=group)
+    dist.broadcast(latents, src=_peer(group, src), group=group)
     return latents
 
 
@@ -53,12 +96,16 @@ def all_gather_ranges(local: torch.Tensor, counts: List[int], group=None) -> tor
     chunks through one all_gather, then trimmed."""
     world = dist.get_world_size(group)
     pad = max(counts) if counts else 0
-    buf = torch.zeros(pad, dtype=local.dtype, device=local.device)
+    staged = _staged(local, group)
+    dev = "cpu" if staged else local.device
+    buf = torch.zeros(pad, dtype=local.dtype, device=dev)
     buf[: local.numel()] = local
-    out = torch.empty(world * pad, dtype=local.dtype, device=local.device)
-    dist.all_gather_into_tensor(out, buf, group=group) if hasattr(dist, "all_gather_into_tensor") and local.is_cuda \
-        else dist.all_gather(list(out.view(world, pad).unbind(0)), buf, group=group)
-    return torch.cat([out[r * pad: r * pad + counts[r]] for r in range(world)])
+    out = torch.empty(world * pad, dtype=local.dtype, device=dev)
+    if buf.is_cuda:
+        dist.all_gather_into_tensor(out, buf, group=group)
+    else:
+        dist.all_gather(list(out.view(world, pad).unbind(0)), buf, group=group)
+    return torch.cat([out[r * pad: r * pad + counts[r]] for r in range(world)]).to(local.device)
 
 
 def decode_dense_sharded(decode_range: Callable[[int, int, torch.Tensor], None], N: Tuple[int, int, int], device,
@@ -77,20 +124,18 @@ def decode_dense_sharded(decode_range: Callable[[int, int, torch.Tensor], None],
     if to_all:
         return all_gather_ranges(local, counts, group).view(n0, n1, n2)
     # one batched group of point-to-point copies (a single NCCL group launch; sizes differ per rank)
-    ops, grid = [], None
+    sends, recvs, grid = [], [], None
     if rank == 0:
         grid = torch.empty(n0 * plane, dtype=torch.float32, device=device)
         grid[: counts[0]] = local
         off = counts[0]
         for r in range(1, world):
             if counts[r]:
-                ops.append(dist.P2POp(dist.irecv, grid[off: off + counts[r]], r, group))
+                recvs.append((grid[off: off + counts[r]], r))
             off += counts[r]
     elif local.numel():
-        ops.append(dist.P2POp(dist.isend, local, 0, group))
-    if ops:
-        for q in dist.batch_isend_irecv(ops):
-            q.wait()
+        sends.append((local, 0))
+    _run_p2p(sends, recvs, group)
     return grid.view(n0, n1, n2) if rank == 0 else None
 
 
@@ -106,45 +151,60 @@ def exchange_halo(local: torch.Tensor, halo: int = MC_HALO, group=None) -> torch
         return local
     if local.shape[0] < halo:
         raise ValueError(f"slab of {local.shape[0]} planes is thinner than the {halo}-plane halo")
-    ops, recv = [], None
+    sends, recv = [], None
     if rank > 0:
-        ops.append(dist.P2POp(dist.isend, local[:halo].contiguous(), rank - 1, group))
+        sends.append((local[:halo], rank - 1))
     if rank < world - 1:
         recv = torch.empty((halo,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-        ops.append(dist.P2POp(dist.irecv, recv, rank + 1, group))
-    for q in dist.batch_isend_irecv(ops):
-        q.wait()
+    _run_p2p(sends, [] if recv is None else [(recv, rank + 1)], group)
     return local if recv is None else torch.cat([local, recv], 0)
 
 
 def extract_mesh_sharded(local: torch.Tensor, plane0: int, count_slab: Callable, emit_slab: Callable, mc_level: float,
-                         group=None, dst: int = 0):
+                         group=None, dst: int = 0, with_halo: bool = False):
     """Marching cubes over a grid that stays partitioned along axis 0.
 
-    local      : this rank's planes [plane0, plane0 + p) of the grid, [p, n1, n2]
+    local      : this rank's planes [plane0, plane0 + p) of the grid, [p, n1, n2]; with ``with_halo`` the tensor
+                 already ends with the next slab's first MC_HALO planes (ranks that decoded or hold them anyway)
     count_slab : (slab_with_halo, own_planes) -> (nV, nF, (vmin, vmax, has_nan))     (MCSurfaceExtractor.count_slab)
     emit_slab  : (nV, nF, plane0, id_base) -> (verts [nV, 3] float32, faces [nF, 3] int32), face ids global
-    Returns (verts, faces) on ``dst`` — exactly the mesh of the whole grid: rank pieces are contiguous ranges of the
-    global lexicographic vertex / face order — and None elsewhere.  Raises the errors of
-    ``skimage.measure.marching_cubes`` (level outside the data range, no surface) on every rank alike."""
+    Returns (verts, faces) on ``dst`` (a group rank) — exactly the mesh of the whole grid: rank pieces are contiguous
+    ranges of the global lexicographic vertex / face order — and None elsewhere.  Raises the errors of
+    ``skimage.measure.marching_cubes`` (level outside the data range, no surface) on every rank alike; a rank whose
+    own kernels fail makes ALL ranks raise before the mesh exchange (nobody is left blocked in a collective)."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    slab = exchange_halo(local, MC_HALO, group)
-    nv, nf, (vmin, vmax, has_nan) = count_slab(slab, local.shape[0])
+    own = local.shape[0] - (MC_HALO if with_halo and rank < world - 1 else 0)
+    slab = local if with_halo else exchange_halo(local, MC_HALO, group)
+    err, nv, nf, vmin, vmax, has_nan = None, 0, 0, float("nan"), float("nan"), False
+    try:
+        nv, nf, (vmin, vmax, has_nan) = count_slab(slab, own)
+    except Exception as e:          # noqa: BLE001 - re-raised below, on every rank
+        err = e
     inf = float("inf")
-    mine = torch.tensor([nv, nf, vmin if vmin == vmin else inf, vmax if vmax == vmax else -inf, float(has_nan)],
-                        dtype=torch.float64, device=local.device)
-    allst = torch.empty((world, 5), dtype=torch.float64, device=local.device)
+    mine = torch.tensor([nv, nf, vmin if vmin == vmin else inf, vmax if vmax == vmax else -inf, float(has_nan), float(err is not None)],
+                        dtype=torch.float64, device="cpu" if _staged(local, group) else local.device)
+    allst = torch.empty((world, 6), dtype=torch.float64, device=mine.device)
     dist.all_gather(list(allst.unbind(0)), mine, group=group)
     allst = allst.cpu()
+    if err is not None:
+        raise err
+    if bool(allst[:, 5].max() > 0):
+        raise RuntimeError("marching cubes failed on another rank of the group")
     nvs, nfs = [int(v) for v in allst[:, 0]], [int(v) for v in allst[:, 1]]
     gmin, gmax, any_nan = float(allst[:, 2].min()), float(allst[:, 3].max()), bool(allst[:, 4].max() > 0)
     if not any_nan and (mc_level < gmin or mc_level > gmax):
         raise ValueError("Surface level must be within volume data range.")
     if sum(nfs) == 0:
         raise RuntimeError("No surface found at the given iso value.")
-    verts, faces = emit_slab(nv, nf, plane0, sum(nvs[:rank]))
+    verts = faces = None
+    try:
+        verts, faces = emit_slab(nv, nf, plane0, sum(nvs[:rank]))
+    except Exception as e:          # noqa: BLE001
+        err = e
+    if not agree(err is None, local.device, group):
+        raise err if err is not None else RuntimeError("marching cubes failed on another rank of the group")
     # mesh pieces -> dst: one batched group of point-to-point copies (sizes differ per rank)
-    ops, V, F = [], None, None
+    sends, recvs, V, F = [], [], None, None
     if rank == dst:
         V = torch.empty((sum(nvs), 3), dtype=torch.float32, device=local.device)
         F = torch.empty((sum(nfs), 3), dtype=torch.int32, device=local.device)
@@ -155,18 +215,16 @@ def extract_mesh_sharded(local: torch.Tensor, plane0: int, count_slab: Callable,
                 F[fo: fo + nfs[r]] = faces
             else:
                 if nvs[r]:
-                    ops.append(dist.P2POp(dist.irecv, V[vo: vo + nvs[r]], r, group))
+                    recvs.append((V[vo: vo + nvs[r]], r))
                 if nfs[r]:
-                    ops.append(dist.P2POp(dist.irecv, F[fo: fo + nfs[r]], r, group))
+                    recvs.append((F[fo: fo + nfs[r]], r))
             vo += nvs[r]; fo += nfs[r]
     else:
         if nv:
-            ops.append(dist.P2POp(dist.isend, verts.contiguous(), dst, group))
+            sends.append((verts, dst))
         if nf:
-            ops.append(dist.P2POp(dist.isend, faces.contiguous(), dst, group))
-    if ops:
-        for q in dist.batch_isend_irecv(ops):
-            q.wait()
+            sends.append((faces, dst))
+    _run_p2p(sends, recvs, group)
     return (V, F) if rank == dst else None
 
 
@@ -181,12 +239,63 @@ def decode_list_sharded(decode_values: Callable[[torch.Tensor], torch.Tensor], i
     return all_gather_ranges(vals, counts, group)
 
 
-class ShardedVanillaVolumeDecoder:
-    """VanillaVolumeDecoder (reference volume_decoders.py:141-182) over a process group; same
-    call signature.  Returns the grid on rank 0 (float32 [B,N,N,N]) and None on the other ranks."""
+class SlabGrid:
+    """A batch of occupancy grids left partitioned along axis 0 across a process group — the opaque grid of SURVEY §8b:
+    it answers ``shape`` / ``len`` / ``[i]`` like the ``[B, N, N, N]`` tensor the reference decoders return, the B200
+    ``MCSurfaceExtractor`` recognises it and extracts the mesh slab by slab (``extract_mesh_sharded``), and
+    ``to_tensor()`` materialises the ordinary tensor on every rank for any other consumer.
 
-    def __init__(self, group=None):
+    slabs[b]  : this rank's planes [plane0, plane0 + own) of item b, followed by the next slab's first MC_HALO planes
+                when ``with_halo`` (ranks that evaluated them anyway), float32 [p, n1, n2]
+    """
+
+    def __init__(self, slabs: List[torch.Tensor], plane0, own, dims: Tuple[int, int, int], with_halo: bool, group=None,
+                 dtype=torch.float32):
+        B = len(slabs)
+        self.slabs, self.dims, self.with_halo, self.group, self.dtype = slabs, tuple(dims), with_halo, group, dtype
+        self.plane0s = list(plane0) if isinstance(plane0, (list, tuple)) else [int(plane0)] * B      # per item: the cuts of a
+        self.owns = list(own) if isinstance(own, (list, tuple)) else [int(own)] * B                  # sparse level differ
+
+    @property
+    def plane0(self) -> int:
+        return self.plane0s[0]
+
+    @property
+    def own(self) -> int:
+        return self.owns[0]
+
+    @property
+    def shape(self):
+        return torch.Size((len(self.slabs),) + self.dims)
+
+    def __len__(self):
+        return len(self.slabs)
+
+    def __getitem__(self, b: int) -> "SlabGrid":
+        return SlabGrid([self.slabs[b]], self.plane0s[b], self.owns[b], self.dims, self.with_halo, self.group, self.dtype)
+
+    def to_tensor(self) -> torch.Tensor:
+        """The whole batch [B, n0, n1, n2] on every rank (one all_gather of the owned planes per item)."""
+        world = dist.get_world_size(self.group)
+        n0, n1, n2 = self.dims
+        B = len(self.slabs)
+        meta = torch.tensor(self.owns, dtype=torch.int64, device="cpu" if _staged(self.slabs[0], self.group) else self.slabs[0].device)
+        owns = torch.empty((world, B), dtype=torch.int64, device=meta.device)
+        dist.all_gather(list(owns.unbind(0)), meta, group=self.group)
+        owns = owns.cpu()
+        return torch.stack([all_gather_ranges(sl[: self.owns[b]].reshape(-1), [int(v) * n1 * n2 for v in owns[:, b]], self.group)
+                            .view(n0, n1, n2) for b, sl in enumerate(self.slabs)], 0).to(self.dtype)
+
+
+class ShardedVanillaVolumeDecoder:
+    """VanillaVolumeDecoder (reference volume_decoders.py:141-182) over a process group; same call signature.
+    ``keep_sharded`` (default): every rank keeps its slab and a ``SlabGrid`` is returned on all ranks — marching cubes
+    then runs per slab behind a two-plane halo exchange (BASELINE config 5).  Otherwise the slabs are gathered and
+    the grid is returned on rank 0 (float32 [B,N,N,N]), None elsewhere."""
+
+    def __init__(self, group=None, keep_sharded: bool = True):
         self.group = group
+        self.keep_sharded = keep_sharded
 
     @torch.no_grad()
     def __call__(self, latents, geo_decoder, bounds=1.01, num_chunks=10000, octree_resolution=None, enable_pbar=True,
@@ -194,24 +303,66 @@ class ShardedVanillaVolumeDecoder:
         ctx = bind(latents, geo_decoder)
         axes = axis_tables(bounds, octree_resolution)
         N = int(octree_resolution) + 1
+        rank, world = dist.get_rank(self.group), dist.get_world_size(self.group)
         outs = []
+        if self.keep_sharded:
+            if N < MC_HALO * world:        # decided identically on every rank: nobody is left waiting in the halo exchange
+                raise ValueError(f"{N} planes cannot be split into {world} slabs of at least {MC_HALO} planes")
+            x0, x1 = slab_planes(N, rank, world)
+            for b in range(latents.shape[0]):
+                ctx.prepare_kv(latents[b])
+                local = torch.empty((x1 - x0, N, N), dtype=torch.float32, device=latents.device)
+                ctx.decode_dense(axes, x0 * N * N, (x1 - x0) * N * N, local)
+                outs.append(local)
+            return SlabGrid(outs, x0, x1 - x0, (N, N, N), False, self.group)
         for b in range(latents.shape[0]):
             ctx.prepare_kv(latents[b])
             g = decode_dense_sharded(lambda first, count, out: ctx.decode_dense(axes, first, count, out), (N, N, N),
                                      latents.device, self.group, to_all=False)
             outs.append(g)
-        if dist.get_rank(self.group) != 0:
+        if rank != 0:
             return None
         return torch.stack(outs, 0)
 
 
+def plane_cuts(index: torch.Tensor, n: int, world: int, halo: int = MC_HALO):
+    """Partition an ordered (lexicographic) active list of an [n,n,n] grid into ``world`` runs of WHOLE planes holding
+    near-equal numbers of queries (variable-thickness slabs = balanced decoder work): the ideal cut
+    r * len / world is moved back to the start of its plane.  Returns host lists (planes, starts, ends): rank r owns
+    planes [planes[r], planes[r+1]) = list entries [starts[r], starts[r+1]) and additionally evaluates the entries up to
+    ends[r] (the actives of the next ``halo`` planes, which its marching-cubes slab needs).  One host read-back.
+    Every slab is at least ``halo`` planes thick (the halo of rank r must lie inside rank r+1's slab)."""
+    cnt, nn = index.numel(), n * n
+    dev = index.device
+    if cnt == 0 or world == 1:
+        planes = [slab_planes(n, r, world)[0] for r in range(world)] + [n]
+    else:
+        pos = torch.tensor([r * cnt // world for r in range(1, world)], device=dev)
+        planes = [0] + [int(v) for v in (index[pos] // nn).cpu()] + [n]
+        for r in range(1, world):                       # strictly increasing by >= halo planes, leaving room for the rest
+            planes[r] = min(max(planes[r], planes[r - 1] + halo), n - halo * (world - r))
+    if any(b - a < halo for a, b in zip(planes, planes[1:])) and world > 1:
+        raise ValueError(f"{n} planes cannot be split into {world} slabs of at least {halo} planes")
+    keys = torch.tensor([p * nn for p in planes] + [min(p + halo, n) * nn for p in planes[1:]], dtype=index.dtype, device=dev)
+    at = [int(v) for v in torch.searchsorted(index, keys).cpu()] if cnt else [0] * (2 * world + 1)
+    return planes, at[: world + 1], at[world + 1:]
+
+
 class ShardedHierarchicalVolumeDecoding:
     """HierarchicalVolumeDecoding (reference :185-277, patched coordinates) over a process group.
-    Every rank ends with the full grid (the next level's active set is recomputed identically
-    everywhere from it); returns it on all ranks."""
 
-    def __init__(self, group=None):
+    Coarse levels: every rank evaluates its share (level 0: an axis-0 slab; refined levels: an equal contiguous range
+    of the ordered active list), the values are all-gathered and every rank holds the whole level — the next active
+    set is derived identically everywhere from it.
+    Last level (``keep_sharded``, default): the active list is cut at plane boundaries into runs of near-equal length;
+    each rank evaluates the queries of its planes plus those of the next two planes (its marching-cubes halo, < 1 %
+    extra work at octree 384 on 8 GPUs), fills only its own slab and returns a ``SlabGrid`` — no all-gather of the
+    values, no full-resolution grid anywhere; the mesh is then extracted slab by slab.  With ``keep_sharded=False`` the
+    last level is gathered like the others and the ordinary tensor is returned on all ranks."""
+
+    def __init__(self, group=None, keep_sharded: bool = True):
         self.group = group
+        self.keep_sharded = keep_sharded
 
     @torch.no_grad()
     def __call__(self, latents, geo_decoder, bounds=1.01, num_chunks=10000, mc_level=0.0, octree_resolution=None,
@@ -220,7 +371,10 @@ class ShardedHierarchicalVolumeDecoding:
         levels = hierarchy_levels(octree_resolution, min_resolution)
         b6 = normalize_bounds(bounds)
         bbox_min, bbox_size = b6[:3], b6[3:] - b6[:3]
-        outs = []
+        bmin32 = bbox_min.astype(np.float32)
+        rank, world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        sharded_last = self.keep_sharded and len(levels) > 1 and levels[-1] + 1 >= MC_HALO * world
+        outs, plane0s, owns = [], [], []
         self.last_stats = []
         for b in range(latents.shape[0]):
             ctx.prepare_kv(latents[b])
@@ -228,23 +382,42 @@ class ShardedHierarchicalVolumeDecoding:
             ax = axis_tables(bounds, levels[0])
             grid = decode_dense_sharded(lambda first, count, out: ctx.decode_dense(ax, first, count, out), (n0, n0, n0),
                                         latents.device, self.group, to_all=True).contiguous()
-            queries = [n0 ** 3]
+            queries, mine = [n0 ** 3], [(slab_planes(n0, rank, world)[1] - slab_planes(n0, rank, world)[0]) * n0 * n0]
             for r in levels[1:]:
-                index = refine_level(ctx, grid, mc_level, last=(r == levels[-1]))
                 n = r + 1
+                last = r == levels[-1]
+                index = refine_level(ctx, grid, mc_level, last=last, nf=n)
                 cell = (bbox_size / r).astype(np.float32)
-
-                def values(idx):
-                    return ctx.decode_list_values(idx, (n, n, n), cell, bbox_min.astype(np.float32))
-                vals = decode_list_sharded(values, index, self.group)
+                queries.append(int(index.numel()))
+                if last and sharded_last:
+                    planes, starts, ends = plane_cuts(index, n, world)
+                    plane0, own = planes[rank], planes[rank + 1] - planes[rank]
+                    p_hi = min(planes[rank + 1] + MC_HALO, n)
+                    part = index[starts[rank]: ends[rank]]
+                    slab = torch.empty((p_hi - plane0, n, n), dtype=torch.float32, device=latents.device)
+                    ctx.fill(slab, SENTINEL)
+                    if part.numel():
+                        vals = ctx.decode_list_values(part, (n, n, n), cell, bmin32)
+                        ctx.scatter(part, vals, slab, base=plane0 * n * n)
+                    ctx.sentinel_to_nan(slab, SENTINEL)
+                    grid = slab
+                    plane0s.append(plane0); owns.append(own)
+                    mine.append(int(part.numel()))
+                    break
+                vals = decode_list_sharded(lambda idx: ctx.decode_list_values(idx, (n, n, n), cell, bmin32), index, self.group)
                 nxt = torch.empty((n, n, n), dtype=torch.float32, device=latents.device)
                 ctx.fill(nxt, SENTINEL)
                 ctx.scatter(index, vals, nxt)
                 grid = nxt
-                queries.append(int(index.numel()))
-            ctx.sentinel_to_nan(grid, SENTINEL)
+                a, bb = list_range(index.numel(), rank, world)
+                mine.append(bb - a)
+            if not sharded_last:
+                ctx.sentinel_to_nan(grid, SENTINEL)
             outs.append(grid)
-            self.last_stats.append({"levels": levels, "queries": queries})
+            self.last_stats.append({"levels": levels, "queries": queries, "rank_queries": mine})
+        if sharded_last:
+            N = levels[-1] + 1
+            return SlabGrid(outs, plane0s, owns, (N, N, N), True, self.group, latents.dtype)
         return torch.stack(outs, 0).to(latents.dtype)
 
 
@@ -253,31 +426,12 @@ def vanilla_latents2mesh_sharded(latents, geo_decoder, surface_extractor=None, g
     """VanillaVolumeDecoder + MCSurfaceExtractor with the grid left in place (BASELINE config 5): every rank decodes
     its slab, marching cubes runs per slab behind a two-plane halo exchange, rank 0 receives the mesh pieces.
     Returns ``list[Latent2MeshOutput | None]`` on rank 0 (the reference's per-item error convention) and None elsewhere."""
-    from .surface_extractors import Latent2MeshOutput, MCSurfaceExtractor
+    from .surface_extractors import MCSurfaceExtractor
     ext = surface_extractor if surface_extractor is not None else MCSurfaceExtractor()
-    rank, world = dist.get_rank(group), dist.get_world_size(group)
-    ctx = bind(latents, geo_decoder)
-    axes = axis_tables(bounds, octree_resolution)
-    N = int(octree_resolution) + 1
-    if N < MC_HALO * world:            # decided identically on every rank: nobody is left waiting in the halo exchange
-        raise ValueError(f"{N} planes cannot be split into {world} slabs of at least {MC_HALO} planes")
-    x0, x1 = slab_planes(N, rank, world)
-    outs = []
-    for b in range(latents.shape[0]):
-        ctx.prepare_kv(latents[b])
-        local = torch.empty((x1 - x0, N, N), dtype=torch.float32, device=latents.device)
-        ctx.decode_dense(axes, x0 * N * N, (x1 - x0) * N * N, local)
-        try:
-            res = extract_mesh_sharded(
-                local, x0, lambda slab, own: ext.count_slab(slab, own, mc_level),
-                lambda nv, nf, p0, base: ext.emit_slab(nv, nf, p0, base, bounds=bounds, octree_resolution=octree_resolution),
-                mc_level, group)
-            outs.append(None if res is None else Latent2MeshOutput(mesh_v=res[0].cpu().numpy(), mesh_f=res[1].cpu().numpy()))
-        except (ValueError, RuntimeError):
-            import traceback
-            traceback.print_exc()
-            outs.append(None)
-    return outs if rank == 0 else None
+    kw = dict(bounds=bounds, mc_level=mc_level, octree_resolution=octree_resolution, **kwargs)
+    grid = ShardedVanillaVolumeDecoder(group, keep_sharded=True)(latents, geo_decoder, **kw)
+    outs = ext(grid, **kw)
+    return outs if dist.get_rank(group) == 0 else None
 
 
 def latents2mesh_data_parallel(vae, latents, group=None, dst: int = 0, **kwargs):

@@ -54,8 +54,10 @@ class SurfaceExtractor:
         for item in range(grid_logits.shape[0]):
             mesh = None
             try:
-                verts, faces = self.run(grid_logits[item], **kwargs)
-                mesh = Latent2MeshOutput(mesh_v=verts.astype(np.float32, copy=False), mesh_f=np.ascontiguousarray(faces))
+                res = self.run(grid_logits[item], **kwargs)
+                if res is not None:           # None: a grid partitioned across GPUs, and this rank is not the mesh's destination
+                    verts, faces = res
+                    mesh = Latent2MeshOutput(mesh_v=verts.astype(np.float32, copy=False), mesh_f=np.ascontiguousarray(faces))
             except Exception:
                 import traceback
                 traceback.print_exc()
@@ -71,6 +73,8 @@ class MCSurfaceExtractor(SurfaceExtractor):
 
     def run_device(self, grid_logit: torch.Tensor, *, mc_level, bounds, octree_resolution, **kwargs):
         """Returns device tensors (verts float32 [V,3], faces int32 [F,3])."""
+        if type(grid_logit).__name__ == "SlabGrid":
+            return self.run_sharded(grid_logit, mc_level=mc_level, bounds=bounds, octree_resolution=octree_resolution, **kwargs)
         if not isinstance(grid_logit, torch.Tensor) or not grid_logit.is_cuda:
             raise RuntimeError("MCSurfaceExtractor needs a CUDA tensor (hy3dgeo has no CPU path)")
         if grid_logit.dim() != 3:
@@ -90,9 +94,21 @@ class MCSurfaceExtractor(SurfaceExtractor):
         return verts, faces
 
     def run(self, grid_logit, *, mc_level, bounds, octree_resolution, **kwargs):
-        verts, faces = self.run_device(grid_logit, mc_level=mc_level, bounds=bounds,
-                                       octree_resolution=octree_resolution, **kwargs)
-        return _to_host(verts, faces)
+        res = self.run_device(grid_logit, mc_level=mc_level, bounds=bounds, octree_resolution=octree_resolution, **kwargs)
+        return None if res is None else _to_host(*res)
+
+    def run_sharded(self, grid, *, mc_level, bounds, octree_resolution, dst: int = 0, **kwargs):
+        """``grid``: a one-item ``hy3dgeo.parallel.SlabGrid`` (the grid stays partitioned along axis 0 across the process
+        group).  Every rank extracts the part of the mesh its planes own; device tensors (verts, faces) of the WHOLE mesh
+        on group rank ``dst``, None elsewhere.  skimage's errors are raised on every rank alike."""
+        from .parallel import extract_mesh_sharded
+        slab = grid.slabs[0]
+        if slab.dim() != 3:
+            raise ValueError("Input volume should be a 3D numpy array.")
+        return extract_mesh_sharded(
+            slab, grid.plane0, lambda s, own: self.count_slab(s, own, mc_level),
+            lambda nv, nf, p0, base: self.emit_slab(nv, nf, p0, base, bounds=bounds, octree_resolution=octree_resolution),
+            mc_level, grid.group, dst, with_halo=grid.with_halo)
 
     # ---- slab forms (hy3dgeo.parallel.extract_mesh_sharded): a grid partitioned along axis 0 ------------------------
     def count_slab(self, slab: torch.Tensor, own_planes: int, mc_level: float):

@@ -107,16 +107,17 @@ class VanillaVolumeDecoder:
         return out
 
 
-def refine_level(ctx: GeoContext, grid: torch.Tensor, mc_level: float, last: bool) -> torch.Tensor:
-    """Ordered flat indices of the fine voxels to query (reference :245-260)."""
+def refine_level(ctx: GeoContext, grid: torch.Tensor, mc_level: float, last: bool, nf: int = None) -> torch.Tensor:
+    """Ordered flat indices of the voxels of the fine grid [nf]^3 to query (reference :245-260).  ``nf`` is the next
+    level's r + 1: 2n-1 when the resolution doubles exactly, 2n when the coarser level is an odd r // 2 (:202-208)."""
     n = grid.shape[0]
-    nf = 2 * n - 1
+    nf = 2 * n - 1 if nf is None else int(nf)
     cap = min(nf ** 3, max(1 << 20, nf ** 3 // 3))
     index = torch.empty(cap, dtype=torch.int32, device=grid.device)
-    cnt = ctx.refine_level(grid, mc_level, last, index)
+    cnt = ctx.refine_level(grid, mc_level, last, index, nf)
     if cnt > cap:
         index = torch.empty(cnt, dtype=torch.int32, device=grid.device)
-        cnt = ctx.refine_level(grid, mc_level, last, index)
+        cnt = ctx.refine_level(grid, mc_level, last, index, nf)
     return index[:cnt]
 
 
@@ -128,7 +129,14 @@ class HierarchicalVolumeDecoding:
     every refined query to (-1,-1,-1); this implements the evident
     intent — the float32 form FlashVDM uses at :394-396 — and is validated against
     the reference class patched the same way.  The reference is batch-1 only
-    (``squeeze(0)``); batches are looped here."""
+    (``squeeze(0)``); batches are looped here.
+
+    ``keep_levels`` (diagnostics / parity tests): keep every level's grid of the last item (sentinel form, -10000 =
+    unvisited) in ``last_levels``."""
+
+    def __init__(self, keep_levels: bool = False):
+        self.keep_levels = keep_levels
+        self.last_levels = []
 
     @torch.no_grad()
     def __call__(self, latents: torch.Tensor, geo_decoder, bounds: Union[Tuple[float], List[float], float] = 1.01,
@@ -146,15 +154,19 @@ class HierarchicalVolumeDecoding:
             grid = torch.empty((n0, n0, n0), dtype=torch.float32, device=latents.device)
             ctx.decode_dense(axis_tables(bounds, levels[0]), 0, n0 ** 3, grid)
             queries = [n0 ** 3]
+            kept = [grid]
             for r in levels[1:]:
-                index = refine_level(ctx, grid, mc_level, last=(r == levels[-1]))
                 n = r + 1
+                index = refine_level(ctx, grid, mc_level, last=(r == levels[-1]), nf=n)
                 nxt = torch.empty((n, n, n), dtype=torch.float32, device=latents.device)
                 ctx.fill(nxt, SENTINEL)
                 cell = (bbox_size / r).astype(np.float32)           # reference :243,:394 float32(resolution)
                 ctx.decode_list(index, index.numel(), (n, n, n), cell, bbox_min.astype(np.float32), nxt)
                 grid = nxt
                 queries.append(int(index.numel()))
+                kept.append(grid)
+            if self.keep_levels:
+                self.last_levels = kept[:-1] + [kept[-1].clone()]
             ctx.sentinel_to_nan(grid, SENTINEL)
             outs.append(grid)
             self.last_stats.append({"levels": levels, "queries": queries})
@@ -207,10 +219,12 @@ class FlashVDMVolumeDecoding:
     sort of their bin id (the reference's ``index.sort()`` is unstable).  ``num_chunks``
     only changes how the reference batches whole bins / mini-grids, never the result: ignored."""
 
-    def __init__(self, topk_mode='mean'):
+    def __init__(self, topk_mode='mean', keep_levels: bool = False):
         if topk_mode not in ['mean', 'merge']:
             raise ValueError(f'Unsupported topk_mode {topk_mode}, available: {["mean", "merge"]}')
         self.topk_mode = topk_mode
+        self.keep_levels = keep_levels        # diagnostics: every level's grid of the last item (sentinel form) in last_levels
+        self.last_levels = []
 
     @torch.no_grad()
     def __call__(self, latents, geo_decoder, bounds=1.01, num_chunks=10000, mc_level=0.0, octree_resolution=None,
@@ -242,10 +256,11 @@ class FlashVDMVolumeDecoding:
             grid = torch.empty((N0, N0, N0), dtype=torch.float32, device=dev)
             ctx.decode_flash(pidx, (N0, N0, N0), tile_group, grid, axes=axes)
             queries = [N0 ** 3]
+            kept = [grid]
             # ---- refined levels: 6^3 spatial bins of the active queries (reference :373-431)
             for r in levels[1:]:
-                index = refine_level(ctx, grid, mc_level, last=(r == levels[-1]))
                 n = r + 1
+                index = refine_level(ctx, grid, mc_level, last=(r == levels[-1]), nf=n)
                 cell = (bbox_size / r).astype(np.float32)
                 bmin32 = bbox_min.astype(np.float32)
                 nxt = torch.empty((n, n, n), dtype=torch.float32, device=dev)
@@ -270,6 +285,9 @@ class FlashVDMVolumeDecoding:
                     ctx.flash_select(sidx, (n, n, n), soff, 216, T, merge, cell=cell, bmin=bmin32)
                     ctx.decode_flash(pidx, (n, n, n), tile_group, nxt, cell=cell, bmin=bmin32)
                 grid = nxt
+                kept.append(grid)
+            if self.keep_levels:
+                self.last_levels = kept[:-1] + [kept[-1].clone()]
             ctx.sentinel_to_nan(grid, SENTINEL)
             outs.append(grid)
             self.last_stats.append({"levels": levels, "queries": queries})

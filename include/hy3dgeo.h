@@ -77,6 +77,11 @@ int hy3d_set_precision(hy3d_ctx* ctx, int precision);
 /* Count of kernels this library has launched on ctx since creation (bench `gpu_launches`). */
 int64_t hy3d_launch_count(const hy3d_ctx* ctx);
 
+/* Which attention kernel the loaded decoder weights select (bench / diagnostics): *h_score_bound = the upper bound of
+ * |q.k| * scale * log2(e) derived from the q/k-norm weights (+inf without q/k norm), *h_bounded_kernel = 1 when the
+ * bounded-score softmax kernel runs, 0 for the online-softmax kernel (csrc/attention_tc.cuh). */
+int hy3d_attention_info(const hy3d_ctx* ctx, float* h_score_bound, int32_t* h_bounded_kernel);
+
 /* ---- latent transformer: replaces ShapeVAE.forward = post_kl + Transformer (model.py:186-189,
  * attention_blocks.py:301-432).  fp32 DEVICE pointers, nn.Linear layout, state_dict names
  * transformer.resblocks.{l}.* (SURVEY App. A.3).  c_qkv_b may be NULL (qkv_bias False). ---------- */
@@ -123,8 +128,10 @@ int hy3d_decode_list(hy3d_ctx* ctx, const int32_t* d_index, int64_t n, int32_t n
  * the ordered list is split across ranks and the values are all-gathered before the scatter). */
 int hy3d_decode_list_values(hy3d_ctx* ctx, const int32_t* d_index, int64_t n, int32_t n0, int32_t n1, int32_t n2,
                             const float h_cell[3], const float h_bmin[3], float* d_values);
-/* d_grid[d_index[q]] = d_values[q] (reference: next_logits[nidx] = grid_logits, volume_decoders.py:273). */
-int hy3d_scatter(hy3d_ctx* ctx, const int32_t* d_index, const float* d_values, int64_t n, float* d_grid);
+/* d_grid[d_index[q] - base] = d_values[q] (reference: next_logits[nidx] = grid_logits, volume_decoders.py:273).
+ * `base` = flat index of d_grid[0] in the whole grid (0, or the first voxel of a slab kept by one GPU);
+ * every non-negative d_index[q] must be >= base.  Entries with d_index[q] < 0 are skipped. */
+int hy3d_scatter(hy3d_ctx* ctx, const int32_t* d_index, const float* d_values, int64_t n, int64_t base, float* d_grid);
 
 /* ---- FlashVDM: replaces FlashVDMVolumeDecoding's decoder calls (volume_decoders.py:343-371,
  * 398-431) and the processors of attention_processors.py:35-96 ------------------------------ */
@@ -154,11 +161,15 @@ int hy3d_flash_group_tokens(hy3d_ctx* ctx, int32_t* d_out, int32_t G);
 /* ---- octree refinement: replaces volume_decoders.py:29-119 and :245-260 / :376-391 ----- */
 /* Active fine voxels of one coarse->fine step: near-surface | band mask,
  * dilation, x2 up-sampling, dilation, ordered compaction.  d_coarse: fp32 [n,n,n] (sentinel
- * -10000 = unvisited).  Writes the lexicographically ordered flat fine indices (grid
- * [2n-1]^3) to d_index (capacity `cap`), returns their number in *h_count (HOST; this
- * call synchronises the stream once).  If the count exceeds cap nothing is written
- * past cap and *h_count still holds the true count. */
-int hy3d_refine_level(hy3d_ctx* ctx, const float* d_coarse, int32_t n, float mc_level, int32_t last_level,
+ * -10000 = unvisited).  The fine grid is [nf]^3 with nf = r + 1 of the next level: 2n-1 when the
+ * resolution doubles exactly, 2n when the coarser level came from an odd r // 2
+ * (volume_decoders.py:202-208, e.g. 390 -> 195 -> 97); up-sampled voxels sit at 2c and the
+ * dilations are clipped at the fine grid's faces, as the zero-padded Conv3d of the reference is.
+ * Writes the lexicographically ordered flat fine indices ((i*nf + j)*nf + k) to d_index
+ * (capacity `cap`), returns their number in *h_count (HOST; this call synchronises the stream
+ * once).  If the count exceeds cap nothing is written past cap and *h_count still holds the
+ * true count. */
+int hy3d_refine_level(hy3d_ctx* ctx, const float* d_coarse, int32_t n, int32_t nf, float mc_level, int32_t last_level,
                       int32_t* d_index, int64_t cap, int64_t* h_count);
 int hy3d_fill(hy3d_ctx* ctx, float* d_grid, int64_t n, float value);
 /* grid[grid == sentinel] = NaN (volume_decoders.py:275, :433). */

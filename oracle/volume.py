@@ -97,15 +97,18 @@ def box3(mask: np.ndarray) -> np.ndarray:
     return out
 
 
-def refine_active_set(grid: np.ndarray, mc_level: float, last: bool) -> np.ndarray:
+def refine_active_set(grid: np.ndarray, mc_level: float, last: bool, nf: int = None) -> np.ndarray:
     """One coarse->fine step of vd:247-260 / vd:378-391.
-    ``grid`` is the coarse level [n,n,n]; returns the boolean fine mask
-    [2n-1, 2n-1, 2n-1] of voxels to query."""
+    ``grid`` is the coarse level [n,n,n]; returns the boolean fine mask [nf,nf,nf]
+    of voxels to query.  ``nf`` = r + 1 of the next level (vd:243): 2n-1 when the
+    resolution doubles exactly (default), 2n when the coarse level is an odd r // 2
+    (vd:202-208); the scatter at 2c (vd:256) and the zero-padded dilations (vd:258)
+    act on that grid."""
     act = (near_surface_mask(grid, mc_level) > 0) | (np.abs(grid) < BAND)
     if not last:
         act = box3(act)
     n = grid.shape[0]
-    nf = 2 * (n - 1) + 1
+    nf = 2 * (n - 1) + 1 if nf is None else int(nf)
     up = np.zeros((nf, nf, nf), dtype=bool)
     cx, cy, cz = np.nonzero(act)
     up[cx * 2, cy * 2, cz * 2] = True
@@ -149,7 +152,7 @@ def hierarchical_decode(decode: Decode, bounds=1.01, num_chunks=10000, mc_level=
     grid = _decode_chunks(decode, dense_points(bounds, levels[0]), num_chunks).reshape(N0, N0, N0)
     stats = {"levels": levels, "queries": [N0 ** 3]}
     for r in levels[1:]:
-        up = refine_active_set(grid, mc_level, last=(r == levels[-1]))
+        up = refine_active_set(grid, mc_level, last=(r == levels[-1]), nf=r + 1)
         idx = np.stack(np.nonzero(up), axis=1)                 # lexicographic (torch.where order)
         vals = _decode_chunks(decode, refined_coords(idx, bounds, r), num_chunks)
         nxt = np.full(up.shape, SENTINEL, dtype=np.float32)

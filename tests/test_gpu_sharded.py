@@ -1,0 +1,150 @@
+"""GPU, world_size 2 on ONE device (two processes sharing cuda:0, gloo for the plumbing — device tensors are staged
+through host memory by hy3dgeo.parallel under gloo): the sharded volume decoders, the slab marching cubes and the
+whole-mesh data-parallel helper run with the real kernels and must reproduce the single-process results bit for bit
+(BASELINE configs 3, 4, 5)."""
+import os
+import socket
+import traceback
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+SPARSE_MINI = (4, 4.0, 0.3)        # oracle/make_golden.py SPARSE["mini"]
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    return port
+
+
+def _same(a: torch.Tensor, b: torch.Tensor) -> bool:
+    """bit equality (NaNs included)"""
+    return a.shape == b.shape and a.dtype == b.dtype and torch.equal(a.contiguous().view(torch.int32), b.contiguous().view(torch.int32))
+
+
+def _worker(rank, world, port, q):
+    try:
+        import torch.distributed as dist
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        import hy3dgeo
+        from hy3dgeo import _lib, parallel as P, weights as W
+        from hy3dgeo.surface_extractors import MCSurfaceExtractor
+        from hy3dgeo.volume_decoders import FlashVDMVolumeDecoding, HierarchicalVolumeDecoding, VanillaVolumeDecoder
+        dev = torch.device("cuda:0")
+        torch.cuda.set_device(dev)
+        cfg = W.MINI
+        sd = W.sparsify_field(W.synthetic_state_dict(cfg, seed=0), cfg, *SPARSE_MINI)
+        vae = hy3dgeo.B200ShapeVAE(cfg, sd, device=dev)
+        z = W.synthetic_latents(cfg, 3, 1234).to(dev)
+        lat = P.broadcast_latents(vae(z) if rank == 0 else None, (3, cfg.num_latents, cfg.width), dev)
+        ctx = _lib.get_context(dev)
+        ext = MCSurfaceExtractor()
+        fails = []
+
+        def check(name, cond):
+            if not cond:
+                fails.append(name)
+
+        # ---- config 3: Hierarchical, 3 levels, last level kept as plane-aligned slabs + slab marching cubes -------
+        for res, minres in [(64, 15), (35, 8)]:
+            kw = dict(bounds=1.01, mc_level=0.0, num_chunks=8000, octree_resolution=res, min_resolution=minres, mc_algo="mc",
+                      enable_pbar=False)
+            dref = HierarchicalVolumeDecoding()
+            ref = dref(lat[:1], vae.geo_decoder, **kw)
+            v_ref, f_ref = ext.run_device(ref[0], mc_level=0.0, bounds=1.01, octree_resolution=res)
+            dec = P.ShardedHierarchicalVolumeDecoding()
+            grid = dec(lat[:1], vae.geo_decoder, **kw)
+            check(f"hier{res}: SlabGrid", isinstance(grid, P.SlabGrid) and tuple(grid.shape) == tuple(ref.shape))
+            st = dec.last_stats[0]
+            check(f"hier{res}: queries", len(st["queries"]) == 3 and st["queries"] == dref.last_stats[0]["queries"])
+            full = grid.to_tensor()
+            check(f"hier{res}: grid bits", _same(full, ref))
+            mesh = ext.run_device(grid[0], mc_level=0.0, bounds=1.01, octree_resolution=res)
+            if rank == 0:
+                check(f"hier{res}: mesh bits", mesh is not None and _same(mesh[0], v_ref) and torch.equal(mesh[1], f_ref))
+            else:
+                check(f"hier{res}: mesh on dst only", mesh is None)
+            outs = ext(grid, **kw)                                       # the plugin call: list per item, numpy on rank 0
+            check(f"hier{res}: plugin call", (outs[0] is not None and np.array_equal(outs[0].mesh_f, f_ref.cpu().numpy())) if rank == 0
+                  else outs == [None])
+            gathered = P.ShardedHierarchicalVolumeDecoding(keep_sharded=False)(lat[:1], vae.geo_decoder, **kw)
+            check(f"hier{res}: gathered variant", isinstance(gathered, torch.Tensor) and _same(gathered, ref))
+        ctx.check_watchdog()
+
+        # ---- config 5: dense Vanilla slabs + halo-exchanged marching cubes ----------------------------------------
+        kw = dict(bounds=[-1.0, -0.9, -0.8, 0.9, 1.0, 1.01], mc_level=0.05, num_chunks=8000, octree_resolution=21, mc_algo="mc",
+                  enable_pbar=False)
+        ref = VanillaVolumeDecoder()(lat[:2], vae.geo_decoder, **kw)
+        grid = P.ShardedVanillaVolumeDecoder()(lat[:2], vae.geo_decoder, **kw)
+        check("vanilla: grid bits", _same(grid.to_tensor(), ref))
+        outs = P.vanilla_latents2mesh_sharded(lat[:2], vae.geo_decoder, **kw)
+        outs_ref = ext(ref, **kw)
+        if rank == 0:
+            for b in range(2):
+                check(f"vanilla: mesh {b}", outs[b] is not None and np.array_equal(outs[b].mesh_f, outs_ref[b].mesh_f)
+                      and np.array_equal(outs[b].mesh_v.view(np.uint32), outs_ref[b].mesh_v.view(np.uint32)))
+        else:
+            check("vanilla: None off rank 0", outs is None)
+        root = P.ShardedVanillaVolumeDecoder(keep_sharded=False)(lat[:2], vae.geo_decoder, **kw)
+        check("vanilla: gathered variant", (_same(root, ref)) if rank == 0 else root is None)
+        # level outside the data range: every rank raises alike, the item becomes None, nobody hangs
+        bad = dict(kw, mc_level=1e6)
+        outs = ext(P.ShardedVanillaVolumeDecoder()(lat[:1], vae.geo_decoder, **bad), **bad)
+        check("vanilla: error convention", outs == [None])
+
+        # ---- config 4: batched latents, whole meshes per rank (FlashVDM) -----------------------------------------
+        vae.volume_decoder = FlashVDMVolumeDecoding("mean")
+        kw = dict(bounds=1.01, mc_level=0.0, num_chunks=8000, octree_resolution=32, min_resolution=15, mc_algo="mc", enable_pbar=False)
+        outs = P.latents2mesh_data_parallel(vae, lat, None, 0, **kw)
+        if rank == 0:
+            seq = vae.latents2mesh(lat, **kw)
+            check("dp: batch order and equality", len(outs) == 3 and all(
+                (a is None) == (b is None) and (a is None or (np.array_equal(a.mesh_f, b.mesh_f) and np.array_equal(a.mesh_v.view(np.uint32), b.mesh_v.view(np.uint32))))
+                for a, b in zip(outs, seq)))
+        else:
+            check("dp: None off dst", outs is None)
+        ctx.check_watchdog()
+        q.put((rank, fails))
+        dist.destroy_process_group()
+    except Exception:
+        q.put((rank, ["EXCEPTION: " + traceback.format_exc()]))
+
+
+def test_sharded_paths_world2_one_device():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=600) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    assert results == {0: [], 1: []}, results
+
+
+def test_plane_cuts_balance_and_cover():
+    from hy3dgeo import parallel as P
+    n = 65
+    g = torch.Generator().manual_seed(3)
+    keep = torch.rand(n ** 3, generator=g) < 0.1
+    keep[: 20 * n * n] = False                                       # empty leading planes
+    index = torch.nonzero(keep).flatten().to(torch.int32).cuda()
+    for world in (1, 2, 3, 8):
+        planes, starts, ends = P.plane_cuts(index, n, world)
+        assert planes[0] == 0 and planes[-1] == n and starts[0] == 0 and starts[-1] == index.numel()
+        assert all(b - a >= P.MC_HALO for a, b in zip(planes, planes[1:])) or world == 1
+        for r in range(world):
+            part = index[starts[r]: starts[r + 1]].long()
+            assert part.numel() == 0 or (int(part.min()) >= planes[r] * n * n and int(part.max()) < planes[r + 1] * n * n)
+            halo = index[starts[r + 1]: ends[r]].long()
+            assert halo.numel() == 0 or int(halo.max()) < min(planes[r + 1] + P.MC_HALO, n) * n * n
+        sizes = [b - a for a, b in zip(starts, starts[1:])]
+        if world > 1:
+            assert max(sizes) - min(sizes) <= 2 * int(keep.view(n, -1).sum(1).max())      # within two planes' worth of the ideal

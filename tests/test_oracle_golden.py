@@ -164,3 +164,83 @@ def test_extractor_rescale_matches_reference_contract(gold):
     assert g["mesh_v"].dtype == np.float32 and g["mesh_f"].dtype == np.int32
     # vertices / (res+1) * size + min : everything inside the (shrunk) box
     assert g["mesh_v"].min() >= -1.01 and g["mesh_v"].max() <= 1.01 * (24 / 25) + 1e-6
+
+
+# ---- round-2 vectors (oracle/make_golden.py r2): BASELINE configurations ---------------------------------------------
+
+def _flash_oracle(gsd, lat, fr, heads, mode, res, minres):
+    proc = OD.FlashProcessorOracle(mode)
+
+    def dec_group(p, topk):
+        proc.topk = topk
+        return OD.geo_decoder_forward(gsd, p, lat.expand(p.shape[0], -1, -1), fr, heads, kv_select=proc)[..., 0]
+    return OV.flashvdm_decode(dec_group, 1.01, 600, 0.0, res, minres, return_stats=True)
+
+
+def test_hierarchical_odd_levels_match_reference(gold):
+    """Levels built with r // 2 (reference vd:202-208) need not double: 35 -> [8, 17, 35] = grids 9, 18 (= 2n), 36 (= 2n).
+    The reference scatters at 2c into the (r+1)^3 grid and dilates with zero padding at ITS faces."""
+    g = gold("volume_analytic_r2.npz")
+    for res, minres in [(35, 8), (45, 10)]:
+        h, st = OV.hierarchical_decode(analytic, 1.01, 20000, 0.0, res, minres, return_stats=True)
+        assert h.shape == (res + 1,) * 3 and st["queries"] == list(g[f"hier{res}_queries"])
+        assert np.array_equal(np.isnan(h), np.isnan(g[f"hier{res}"]))
+        assert np.array_equal(np.nan_to_num(h), np.nan_to_num(g[f"hier{res}"]))
+    assert OV.hierarchy_levels(390) == [97, 195, 390] and OV.hierarchy_levels(70, 15) == [17, 35, 70]
+    _, st = OV.hierarchical_decode(analytic, 1.01, 200000, 0.0, 70, 15, return_stats=True)
+    assert st["queries"] == list(g["hier70_queries"])
+
+
+def test_three_level_hierarchical_and_mesh_on_real_decoder(gold, checksum):
+    """3 levels with expand_num=1 on the middle one (vd:250-259) and odd levels on the real mini decoder; the octree-64
+    dense field gives the >= 10k-vertex end-to-end mesh the reference's latents2mesh produced (MC = oracle, unpinned)."""
+    cfg = W.MINI
+    g = gold("volume_decoder_mini_r2.npz")
+    sd = W.sparsify_field(W.synthetic_state_dict(cfg, seed=0), cfg, int(g["keep_freqs"]), float(g["gain"]), float(g["bias"]))
+    assert checksum(sd) == pytest.approx(float(g["weight_checksum"]), rel=1e-9)
+    lat = OD.shapevae_forward(sd, W.synthetic_latents(cfg, 1, 1234), cfg.heads)
+    gsd, fr = W.geo_decoder_state(sd), W.fourier_frequencies(cfg)
+    dec = lambda p: OD.geo_decoder_forward(gsd, p[None], lat, fr, cfg.dec_heads)[0, :, 0]
+    for res, minres in [(64, 15), (35, 8)]:
+        h, st = OV.hierarchical_decode(dec, 1.01, 8000, 0.0, res, minres, return_stats=True)
+        ref = g[f"hier{res}"]
+        assert len(st["levels"]) == 3 and st["queries"] == list(g[f"hier{res}_queries"])
+        assert np.array_equal(np.isnan(h), np.isnan(ref))
+        assert np.abs(np.nan_to_num(h) - np.nan_to_num(ref)).max() < 5e-5
+    m = gold("latents2mesh_mini64.npz")
+    assert m["mesh_v"].shape[0] >= 10000 and m["mesh_f"].max() == m["mesh_v"].shape[0] - 1
+    grid = OV.vanilla_decode(dec, 1.01, 8000, 64)
+    v, f = OM.mc_surface_extract(grid, mc_level=0.0, bounds=1.01, octree_resolution=64)
+    assert np.array_equal(f, m["mesh_f"]) and np.abs(v - m["mesh_v"]).max() < 1e-4
+
+
+@pytest.mark.parametrize("tag,res", [("turbo", 32), ("turbo", 64), ("full", 32)])
+def test_flashvdm_turbo_and_full_match_reference(tag, res, gold, checksum):
+    """BASELINE config 4 (mini-turbo: no q/k norm, latents_proj, expand 1, top-256) and the full decoder (top-1024,
+    attention_processors.py:40-45), both selection modes."""
+    cfg = CFG[tag]
+    g = gold(f"flash_{tag}.npz")
+    sd = W.sparsify_field(W.synthetic_state_dict(cfg, seed=0), cfg, int(g["keep_freqs"]), float(g["gain"]), float(g["bias"]))
+    assert checksum(sd) == pytest.approx(float(g["weight_checksum"]), rel=1e-9)
+    torch.set_num_threads(8)
+    lat = OD.shapevae_forward(sd, W.synthetic_latents(cfg, 1, 1234), cfg.heads)
+    gsd, fr = W.geo_decoder_state(sd), W.fourier_frequencies(cfg)
+    for mode in ("mean", "merge"):
+        f, st = _flash_oracle(gsd, lat, fr, cfg.dec_heads, mode, res, 15)
+        ref = g[f"flash{res}_{mode}"]
+        assert st["queries"] == list(g[f"flash{res}_{mode}_queries"])
+        assert np.array_equal(np.isnan(f), np.isnan(ref))
+        assert np.abs(np.nan_to_num(f) - np.nan_to_num(ref)).max() < 5e-5 * max(1.0, float(g["gain"]) / 6.0)
+
+
+def test_decoder_include_pi_matches_reference(gold, checksum):
+    import dataclasses
+    cfg = dataclasses.replace(W.MINI, include_pi=True)
+    g = gold("decoder_pi.npz")
+    sd = W.synthetic_state_dict(cfg, seed=0)
+    assert checksum(sd) == pytest.approx(float(g["weight_checksum"]), rel=1e-9)
+    fr = W.fourier_frequencies(cfg)
+    assert abs(float(fr[0]) - np.pi) < 1e-6
+    lat = OD.shapevae_forward(sd, W.synthetic_latents(cfg, 1, 1234), cfg.heads)
+    out = OD.geo_decoder_forward(W.geo_decoder_state(sd), torch.from_numpy(g["queries"]), lat, fr, cfg.dec_heads)[0, :, 0]
+    assert np.abs(out.numpy() - g["logits"]).max() < 2e-5
