@@ -9,10 +9,10 @@ raises if ``libhy3dgeo.so`` is missing.
 from . import weights, utils, _lib, volume_decoders, surface_extractors, model  # noqa: F401
 from .model import B200ShapeVAE, GeoDecoder, install, enable_flashvdm_decoder  # noqa: F401
 from .surface_extractors import (DMCSurfaceExtractor, Latent2MeshOutput, MCSurfaceExtractor,  # noqa: F401
-                                 SurfaceExtractor, SurfaceExtractors)
+                                 SurfaceExtractor, SurfaceExtractors, export_to_trimesh)
 from .volume_decoders import (FlashVDMVolumeDecoding, HierarchicalVolumeDecoding,  # noqa: F401
                               VanillaVolumeDecoder)
 
 __all__ = ["B200ShapeVAE", "GeoDecoder", "install", "enable_flashvdm_decoder", "VanillaVolumeDecoder",
            "HierarchicalVolumeDecoding", "FlashVDMVolumeDecoding", "MCSurfaceExtractor", "DMCSurfaceExtractor",
-           "SurfaceExtractor", "SurfaceExtractors", "Latent2MeshOutput"]
+           "SurfaceExtractor", "SurfaceExtractors", "Latent2MeshOutput", "export_to_trimesh"]

@@ -95,6 +95,8 @@ SYMBOLS = {
                                      C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_float)]),
     "hy3d_mc_emit_slab": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                     C.c_int32, C.c_int64, c_f32p, c_i32p]),
+    "hy3d_mesh_clean": (C.c_int, [C.c_void_p, c_f32p, C.c_int64, c_i32p, C.c_int64, C.c_int32, c_f32p, c_i32p,
+                                  C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "hy3d_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "hy3d_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "hy3d_debug_watchdog": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
@@ -192,6 +194,15 @@ class GeoContext:
         and points at it.  id() / data_ptr() values alone are not identities: CPython and the caching allocator
         hand the same values to new objects once the old ones are freed."""
         return owner is not None and ref is not None and ref() is owner
+
+    def has_decoder(self, key, owner) -> bool:
+        """True when the decoder weights cached in this context were loaded from `owner` under the same `key`."""
+        return key is not None and key == self._weights_key and self._same_owner(getattr(self, "_weights_owner", None), owner)
+
+    def invalidate_weights(self):
+        """Forget the cached decoder / transformer weights (after an edit through ``param.data``, which no key can see)."""
+        self._weights_key = None
+        self._tf_key = None
 
     def set_decoder(self, sd, cfg, key=None, owner=None):
         """sd: decoder state dict (keys without ``geo_decoder.``), cfg: ShapeVAEConfig.  `key` (+ the live `owner`
@@ -461,6 +472,17 @@ class GeoContext:
         m = (C.c_double * 3)(*[float(v) for v in mul])
         a = (C.c_double * 3)(*[float(v) for v in add])
         self._check(self.lib.hy3d_mc_emit_slab(self.h, d, m, a, int(plane0), int(id_base), _ptr(verts), _ptr(faces)), "hy3d_mc_emit_slab")
+
+    def mesh_clean(self, verts: torch.Tensor, faces: torch.Tensor, flip_winding: bool):
+        """Device tensors (verts float32 [V,3], faces int32 [F,3]) -> the same mesh without non-finite / unreferenced
+        vertices and the faces that used them, winding optionally reversed (see hy3dgeo.h: hy3d_mesh_clean)."""
+        self.sync_stream()
+        verts, faces = verts.contiguous(), faces.contiguous()
+        vo, fo = torch.empty_like(verts), torch.empty_like(faces)
+        nv, nf = C.c_int64(), C.c_int64()
+        self._check(self.lib.hy3d_mesh_clean(self.h, _ptr(verts), verts.shape[0], _ptr(faces), faces.shape[0], int(bool(flip_winding)),
+                                             _ptr(vo), _ptr(fo), C.byref(nv), C.byref(nf)), "hy3d_mesh_clean")
+        return vo[: nv.value], fo[: nf.value]
 
     def mc_cases(self, grid: torch.Tensor, level: float) -> torch.Tensor:
         self.sync_stream()

@@ -93,6 +93,32 @@ int hy3d_debug_fetch(hy3d_ctx* ctx, int stage, float* d_out, int64_t rows, int32
   return HY3D_OK;
 }
 
+}  // extern "C"
+
+// The tables are a few KB and change only with (bounds, resolution): they are kept in ws[11] and re-uploaded only when
+// their contents differ from the last upload.  Then the stream is drained first (kernels of earlier calls may still read
+// the old tables) and the copy is synchronous (pageable source) — the common repeated call costs no synchronisation.
+int hy3d_upload_axes(hy3d_ctx* ctx, const float* h0, const float* h1, const float* h2, int n0, int n1, int n2) {
+  const size_t na = (size_t)n0 + n1 + n2;
+  std::vector<float>& tab = ctx->axis_host;
+  const bool same = tab.size() == na + 3 && tab[0] == (float)n0 && tab[1] == (float)n1 && tab[2] == (float)n2 &&
+                    !memcmp(tab.data() + 3, h0, n0 * sizeof(float)) && !memcmp(tab.data() + 3 + n0, h1, n1 * sizeof(float)) &&
+                    !memcmp(tab.data() + 3 + n0 + n1, h2, n2 * sizeof(float)) && ctx->ws[11].p;
+  if (same) return 0;
+  HY3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  HY3D_CUDA(ctx, ctx->ws[11].reserve(na * sizeof(float)));
+  tab.resize(na + 3);
+  tab[0] = (float)n0; tab[1] = (float)n1; tab[2] = (float)n2;
+  memcpy(tab.data() + 3, h0, n0 * sizeof(float));
+  memcpy(tab.data() + 3 + n0, h1, n1 * sizeof(float));
+  memcpy(tab.data() + 3 + n0 + n1, h2, n2 * sizeof(float));
+  HY3D_CUDA(ctx, cudaMemcpyAsync(ctx->ws[11].p, tab.data() + 3, na * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  HY3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+extern "C" {
+
 int hy3d_create(int device, void* cuda_stream, hy3d_ctx** out) {
   if (!out) return HY3D_ERR_ARG;
   *out = nullptr;
@@ -251,15 +277,7 @@ int hy3d_decode_dense(hy3d_ctx* ctx, const float* h0, const float* h1, const flo
   if (count == 0) return HY3D_OK;
   if (!d_out) return HY3D_ERR_ARG;
   HY3D_CUDA(ctx, cudaSetDevice(ctx->device));
-  size_t na = (size_t)n0 + n1 + n2;
-  HY3D_CUDA(ctx, ctx->ws[11].reserve(na * sizeof(float)));
-  std::vector<float> tab(na);
-  memcpy(tab.data(), h0, n0 * sizeof(float));
-  memcpy(tab.data() + n0, h1, n1 * sizeof(float));
-  memcpy(tab.data() + n0 + n1, h2, n2 * sizeof(float));
-  // small synchronous upload (pageable source): completes before return, so `tab` may die
-  HY3D_CUDA(ctx, cudaMemcpyAsync(ctx->ws[11].p, tab.data(), na * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-  HY3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (int rc = hy3d_upload_axes(ctx, h0, h1, h2, n0, n1, n2)) return rc;
   QuerySource s{};
   s.mode = 1; s.axis = ctx->ws[11].as<float>(); s.n0 = n0; s.n1 = n1; s.n2 = n2; s.first = first;
   return decode(ctx, s, count, d_out, 0);

@@ -3,8 +3,14 @@
 // head dim 64, 128-query tiles, fp16 operands, fp32 accumulation in tensor memory.
 // Included by decoder_tc.cu inside its anonymous namespace (uses TILE_BYTES, store_t16_* and tc::).
 //
-// One CTA iteration = one 128-query tile x 2 heads; each head is an independent *stream* with its own
-//   producer warp  (warp 2a):   Q tile, then K(0), K(1), V(0), K(2), V(1), ... through a ring of 16 KB slots
+// One CTA iteration = two independent *streams* of one (128-query tile, head) each:
+//   share_kv = 1 (plain decoding, the latent transformer): the two streams are two QUERY TILES of the SAME head and consume
+//                the same K / V^T tiles from ONE ring of 10 slots, loaded once by one producer warp — half the L2 -> SM
+//                traffic and half the shared-memory fill bandwidth of giving each stream its own copy (the K/V of a head
+//                used to be re-streamed from L2 for every 128 queries: ~31 B/clk/SM, three quarters of the L2 ceiling);
+//   share_kv = 0 (FlashVDM: neighbouring query tiles may belong to different KV groups): the two streams are two HEADS of
+//                one query tile, each with its own producer warp and ring of 5 slots.
+//   producer warp  (warp 0 / 2a): Q tile(s), then K(0), K(1), V(0), K(2), V(1), ... through a ring of 16 KB slots
 //                               (1-D bulk copies: every tile is one contiguous SW128 K-major image)
 //   MMA warp       (warp 2a+1): S = Q K(j)^T  (4 x tcgen05.mma 128x128x16, A and B from shared memory)
 //                               O += P(j) V(j) (8 x tcgen05.mma 128x64x16, A = P from TENSOR memory, B = V^T)
@@ -45,6 +51,7 @@ struct AttnTC {
   const int* group_ntok; // valid tokens per group or null
   int Pb, H, nkv, ntok;  // nkv = tiles per (group, head); ntok = valid tokens when group_ntok == null
   int split_out;         // O written as [hi | lo | hi] over 3H k-blocks (operand of a 3-term split GEMM)
+  int share_kv;          // 1: streams = two query tiles of one head sharing every K/V tile; 0: two heads of one query tile
   unsigned long long* timers;   // k_attn_fast<.., true>: phase clocks of CTA 0 (see hy3d_debug_timers)
 };
 
@@ -53,6 +60,9 @@ struct AttnBars {                          // mbarrier addresses (shared window)
   static constexpr int NB = 2 * ATT_SLOTS + 6;
   __device__ __forceinline__ uint32_t kvfull(int a, int s) const { return b0 + 8u * (a * NB + s); }
   __device__ __forceinline__ uint32_t kvempty(int a, int s) const { return b0 + 8u * (a * NB + ATT_SLOTS + s); }
+  // shared ring (share_kv): slot s in [0, 2 SLOTS) uses stream (s / SLOTS)'s barrier s % SLOTS
+  __device__ __forceinline__ uint32_t kvfull_sh(int s) const { return kvfull(s >= ATT_SLOTS, s >= ATT_SLOTS ? s - ATT_SLOTS : s); }
+  __device__ __forceinline__ uint32_t kvempty_sh(int s) const { return kvempty(s >= ATT_SLOTS, s >= ATT_SLOTS ? s - ATT_SLOTS : s); }
   __device__ __forceinline__ uint32_t qfull(int a) const { return b0 + 8u * (a * NB + 2 * ATT_SLOTS); }
   __device__ __forceinline__ uint32_t qempty(int a) const { return b0 + 8u * (a * NB + 2 * ATT_SLOTS + 1); }
   __device__ __forceinline__ uint32_t sfull(int a) const { return b0 + 8u * (a * NB + 2 * ATT_SLOTS + 2); }
@@ -65,14 +75,14 @@ constexpr int ATT_TILES_BYTES = (2 + 2 * ATT_SLOTS) * TILE_BYTES;      // Q[2] +
 constexpr size_t ATT_SMEM = 1024 + ATT_TILES_BYTES + 512 + 2048;       // + barriers / TMEM slot + row-sum exchange (fast kernel)
 
 // Shared prologue: barriers, TMEM.  `softmax_warps` = arrivals expected on SEMPTY / PFULL per stream.
-__device__ __forceinline__ uint32_t attn_setup(uint8_t* smem, AttnBars& B, int softmax_warps) {
+__device__ __forceinline__ uint32_t attn_setup(uint8_t* smem, AttnBars& B, int softmax_warps, int share_kv) {
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATT_TILES_BYTES);
   B.b0 = smem_u32(bars);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * AttnBars::NB);
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     for (int a = 0; a < 2; ++a) {
-      for (int s = 0; s < ATT_SLOTS; ++s) { mbar_init(B.kvfull(a, s), 1); mbar_init(B.kvempty(a, s), 1); }
+      for (int s = 0; s < ATT_SLOTS; ++s) { mbar_init(B.kvfull(a, s), 1); mbar_init(B.kvempty(a, s), share_kv ? 2 : 1); }   // shared slot: released by both streams' MMAs
       mbar_init(B.qfull(a), 1); mbar_init(B.qempty(a), 1);
       mbar_init(B.sfull(a), 1); mbar_init(B.sempty(a), softmax_warps); mbar_init(B.pfull(a), softmax_warps); mbar_init(B.pvdone(a), 1);
     }
@@ -85,33 +95,54 @@ __device__ __forceinline__ uint32_t attn_setup(uint8_t* smem, AttnBars& B, int s
   return *tmem_slot;
 }
 
-// Producer warp of stream a (whole warp converged).
+// Work item -> (query tile, head) of stream a.  share_kv: item = (pair of query tiles, head), stream a takes tile 2 pair + a
+// (an odd tile count leaves the last pair's second stream on a duplicate of the last tile; it computes but does not store).
+struct AttnItem { int qt, h; bool store; };
+__device__ __forceinline__ int attn_num_items(const AttnTC& g) { return g.share_kv ? ((g.Pb + 1) >> 1) * g.H : g.Pb * (g.H >> 1); }
+__device__ __forceinline__ AttnItem attn_item(const AttnTC& g, int item, int a) {
+  AttnItem it;
+  if (g.share_kv) {
+    const int pr = item / g.H, q = 2 * pr + a;
+    it.h = item - pr * g.H; it.store = q < g.Pb; it.qt = it.store ? q : g.Pb - 1;
+  } else {
+    const int HP = g.H >> 1;
+    it.qt = item / HP; it.h = (item - it.qt * HP) * 2 + a; it.store = true;
+  }
+  return it;
+}
+
+// Producer warp of stream a (whole warp converged).  share_kv: called once (a = 0) and feeds both streams.
 __device__ __forceinline__ void attn_producer(const AttnTC& g, const AttnBars& B, uint8_t* smem, int a) {
-  uint8_t* sQ = smem + a * TILE_BYTES;
-  uint8_t* ring = smem + 2 * TILE_BYTES + a * ATT_SLOTS * TILE_BYTES;
-  const int HP = g.H / 2, nitems = g.Pb * HP, nkv = g.nkv;
+  const bool sh = g.share_kv != 0;
+  uint8_t* ring = smem + 2 * TILE_BYTES + (sh ? 0 : a * ATT_SLOTS * TILE_BYTES);
+  const int nslots = sh ? 2 * ATT_SLOTS : ATT_SLOTS;
+  const int nitems = attn_num_items(g), nkv = g.nkv;
   int s = 0; uint32_t ph = 0, qph = 0;
   auto push = [&](const uint8_t* src) {
-    mbar_wait(B.kvempty(a, s), ph ^ 1);
+    const uint32_t full = sh ? B.kvfull_sh(s) : B.kvfull(a, s), empty = sh ? B.kvempty_sh(s) : B.kvempty(a, s);
+    mbar_wait(empty, ph ^ 1);
     if (elect_one()) {
-      mbar_arrive_expect_tx(B.kvfull(a, s), TILE_BYTES);
-      bulk_g2s(smem_u32(ring + s * TILE_BYTES), src, TILE_BYTES, B.kvfull(a, s));
+      mbar_arrive_expect_tx(full, TILE_BYTES);
+      bulk_g2s(smem_u32(ring + s * TILE_BYTES), src, TILE_BYTES, full);
     }
     __syncwarp();
-    if (++s == ATT_SLOTS) { s = 0; ph ^= 1; }
+    if (++s == nslots) { s = 0; ph ^= 1; }
   };
   for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-    const int qt = item / HP, h = (item % HP) * 2 + a;
-    const int grp = g.tile_group ? g.tile_group[qt] : 0;
-    mbar_wait(B.qempty(a), qph ^ 1);
-    if (elect_one()) {
-      mbar_arrive_expect_tx(B.qfull(a), TILE_BYTES);
-      bulk_g2s(smem_u32(sQ), g.Q + ((size_t)qt * g.H + h) * TILE_BYTES, TILE_BYTES, B.qfull(a));
+    AttnItem it = attn_item(g, item, a);
+    for (int aa = a; aa < (sh ? 2 : a + 1); ++aa) {           // Q tile of each stream this producer feeds
+      const AttnItem iq = attn_item(g, item, aa);
+      mbar_wait(B.qempty(aa), qph ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(B.qfull(aa), TILE_BYTES);
+        bulk_g2s(smem_u32(smem + aa * TILE_BYTES), g.Q + ((size_t)iq.qt * g.H + iq.h) * TILE_BYTES, TILE_BYTES, B.qfull(aa));
+      }
+      __syncwarp();
     }
-    __syncwarp();
     qph ^= 1;
-    const uint8_t* kb = g.K + ((size_t)grp * g.H + h) * nkv * TILE_BYTES;
-    const uint8_t* vb = g.V + ((size_t)grp * g.H + h) * nkv * TILE_BYTES;
+    const int grp = g.tile_group ? g.tile_group[it.qt] : 0;
+    const uint8_t* kb = g.K + ((size_t)grp * g.H + it.h) * nkv * TILE_BYTES;
+    const uint8_t* vb = g.V + ((size_t)grp * g.H + it.h) * nkv * TILE_BYTES;
     push(kb);
     for (int j = 0; j < nkv; ++j) {
       if (j + 1 < nkv) push(kb + (size_t)(j + 1) * TILE_BYTES);
@@ -122,42 +153,56 @@ __device__ __forceinline__ void attn_producer(const AttnTC& g, const AttnBars& B
 
 // MMA-issuing warp of stream a (whole warp converged, one elected lane issues).
 __device__ __forceinline__ void attn_mma(const AttnTC& g, const AttnBars& B, uint8_t* smem, uint32_t tmem, int a) {
+  const bool sh = g.share_kv != 0;
   uint8_t* sQ = smem + a * TILE_BYTES;
-  uint8_t* ring = smem + 2 * TILE_BYTES + a * ATT_SLOTS * TILE_BYTES;
-  const int HP = g.H / 2, nitems = g.Pb * HP, nkv = g.nkv;
+  uint8_t* ring = smem + 2 * TILE_BYTES + (sh ? 0 : a * ATT_SLOTS * TILE_BYTES);
+  const int nslots = sh ? 2 * ATT_SLOTS : ATT_SLOTS;
+  const int nitems = attn_num_items(g), nkv = g.nkv;
   const uint32_t idesc_s = make_idesc_f16(128, 128);
   const uint32_t idesc_o = make_idesc_f16(128, 64);
   const uint32_t d_s = tmem + TM_S0 + a * 128, d_o = tmem + TM_O0 + a * 64, a_p = tmem + TM_P0 + a * 64;
   const uint64_t qd = make_desc_sw128(smem_u32(sQ));
   int s = 0; uint32_t ph = 0, qph = 0, sph = 0, pph = 0;
+  // instrumented launches (hy3d_debug_timers): cycles this warp waits for 0 K tile, 1 S buffer free, 2 V tile, 3 P stored
+  const bool tmr = g.timers != nullptr && blockIdx.x == 0;
+  long long tw[4] = {0, 0, 0, 0}, t0 = 0;
+  auto tick = [&](int i) { if (tmr) { const long long t_ = clock64(); tw[i] += t_ - t0; t0 = t_; } };
   auto issue_s = [&]() {
-    mbar_wait(B.kvfull(a, s), ph);
+    const uint32_t full = sh ? B.kvfull_sh(s) : B.kvfull(a, s), empty = sh ? B.kvempty_sh(s) : B.kvempty(a, s);
+    if (tmr) t0 = clock64();
+    mbar_wait(full, ph);
+    tick(0);
     mbar_wait(B.sempty(a), sph ^ 1); sph ^= 1;
+    tick(1);
     fence_after_sync();
     const uint64_t bd = make_desc_sw128(smem_u32(ring + s * TILE_BYTES));
     if (elect_one()) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) mma_f16_ss(d_s, qd + 2 * k, bd + 2 * k, idesc_s, k != 0);
-      mma_commit(B.kvempty(a, s));
+      mma_commit(empty);
       mma_commit(B.sfull(a));
     }
     __syncwarp();
-    if (++s == ATT_SLOTS) { s = 0; ph ^= 1; }
+    if (++s == nslots) { s = 0; ph ^= 1; }
   };
   auto issue_pv = [&](int j) {
-    mbar_wait(B.kvfull(a, s), ph);
+    const uint32_t full = sh ? B.kvfull_sh(s) : B.kvfull(a, s), empty = sh ? B.kvempty_sh(s) : B.kvempty(a, s);
+    if (tmr) t0 = clock64();
+    mbar_wait(full, ph);
+    tick(2);
     mbar_wait(B.pfull(a), pph); pph ^= 1;
+    tick(3);
     fence_after_sync();
     const uint64_t bd = make_desc_sw128(smem_u32(ring + s * TILE_BYTES));
     if (elect_one()) {
 #pragma unroll
       for (int k = 0; k < 8; ++k)                      // 16 tokens (8 TMEM columns of fp16 pairs) per MMA
         mma_f16_ts(d_o, a_p + 8 * k, bd + (k >> 2) * (TILE_BYTES / 2 / 16) + 2 * (k & 3), idesc_o, (j | k) != 0);
-      mma_commit(B.kvempty(a, s));
+      mma_commit(empty);
       mma_commit(B.pvdone(a));
     }
     __syncwarp();
-    if (++s == ATT_SLOTS) { s = 0; ph ^= 1; }
+    if (++s == nslots) { s = 0; ph ^= 1; }
   };
   for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
     mbar_wait(B.qfull(a), qph); qph ^= 1;
@@ -169,6 +214,8 @@ __device__ __forceinline__ void attn_mma(const AttnTC& g, const AttnBars& B, uin
       issue_pv(j);
     }
   }
+  if (tmr && (threadIdx.x & 31) == 0)
+    for (int i = 0; i < 4; ++i) atomicAdd(&g.timers[16 + a * 4 + i], (unsigned long long)tw[i]);
 }
 
 // exp2 on the FMA/ALU pipes (Cody-Waite split + degree-3 minimax on [-0.5, 0.5], max rel. error 1.6e-4, below the
@@ -184,10 +231,33 @@ __device__ __forceinline__ float exp2_poly(float x) {
 }
 template <int kPoly>
 __device__ __forceinline__ bool exp_on_fma(int i) {
-  // 16-element patterns: kPoly 1 = 2/16, 5 = 3/16, 2 = 4/16, 3 = 6/16, 4 = 8/16
+  // 16-element patterns of the online-softmax kernel: kPoly 1 = 2/16, 5 = 3/16, 2 = 4/16, 3 = 6/16, 4 = 8/16
   constexpr unsigned kMask = kPoly == 0 ? 0x0000u : kPoly == 1 ? 0x1010u : kPoly == 5 ? 0x0842u : kPoly == 2 ? 0x2222u : kPoly == 3 ? 0x5252u
                            : kPoly == 4 ? 0xAAAAu : 0xEEEEu;
   return ((kMask >> (i & 15)) & 1u) != 0;
+}
+// Bounded-score kernel: whole PAIRS of adjacent exponentials go to the FMA pipe so that the polynomial runs on packed
+// f32x2 instructions (FADD2 / FFMA2: both lanes for one issue slot) — kPairs of every 8 pairs (= 2 kPairs / 16 elements).
+template <int kPairs>
+__device__ __forceinline__ bool pair_on_fma(int pair) {
+  constexpr unsigned kMask = kPairs <= 0 ? 0x00u : kPairs == 1 ? 0x10u : kPairs == 2 ? 0x44u : kPairs == 3 ? 0x54u : 0xAAu;
+  return ((kMask >> (pair & 7)) & 1u) != 0;
+}
+// exp2 of two finite scores (|x| <= 15.9, no clamp needed) on the FMA pipe: 3 FADD2 + 3 FFMA2 + 2 integer ops for the pair
+__device__ __forceinline__ void exp2_poly2(float x0, float x1, float& p0, float& p1) {
+  const uint64_t kMagic = pack_f2(12582912.f, 12582912.f);
+  const uint64_t c3 = pack_f2(5.360121652e-02f, 5.360121652e-02f), c2 = pack_f2(2.423726171e-01f, 2.423726171e-01f);
+  const uint64_t c1 = pack_f2(6.935024858e-01f, 6.935024858e-01f), c0 = pack_f2(9.999481440e-01f, 9.999481440e-01f);
+  const uint64_t x = pack_f2(x0, x1);
+  const uint64_t t = add_f2(x, kMagic);                // integer part in the low mantissa bits
+  const uint64_t f = sub_f2(x, sub_f2(t, kMagic));     // fraction in [-0.5, 0.5]
+  uint64_t p = fma_f2(c3, f, c2);
+  p = fma_f2(p, f, c1);
+  p = fma_f2(p, f, c0);
+  float pa, pb, ta, tb;
+  unpack_f2(p, pa, pb); unpack_f2(t, ta, tb);
+  p0 = __int_as_float(__float_as_int(pa) + (__float_as_int(ta) << 23));
+  p1 = __int_as_float(__float_as_int(pb) + (__float_as_int(tb) << 23));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -198,15 +268,15 @@ __global__ void __launch_bounds__(ATT_FAST_THREADS, 1) k_attn_fast(AttnTC g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   AttnBars B;
-  const uint32_t tmem = attn_setup(smem, B, 8);
+  const uint32_t tmem = attn_setup(smem, B, 8, g.share_kv);
   float* lsum = reinterpret_cast<float*>(smem + ATT_TILES_BYTES + 512);   // [2 streams][2 halves][128 rows]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int HP = g.H / 2, nitems = g.Pb * HP, nkv = g.nkv;
+  const int nitems = attn_num_items(g), nkv = g.nkv;
 
   // (no setmaxnreg here: registers can only be moved inside the CTA's launch allocation, 640 x 96, and the
   //  softmax threads fit in 96)
   if (warp < 4) {
-    if ((warp & 1) == 0) attn_producer(g, B, smem, warp >> 1);
+    if ((warp & 1) == 0) { if (!g.share_kv || warp == 0) attn_producer(g, B, smem, warp >> 1); }   // shared ring: one producer
     else attn_mma(g, B, smem, tmem, warp >> 1);
   } else {
     const int a = (warp - 4) >> 3;                      // head stream
@@ -221,12 +291,19 @@ __global__ void __launch_bounds__(ATT_FAST_THREADS, 1) k_attn_fast(AttnTC g) {
     long long tk0 = 0, tk[6] = {0, 0, 0, 0, 0, 0};
 #define HY3D_TICK(i) if constexpr (kTimers) { const long long t_ = clock64(); tk[i] += t_ - tk0; tk0 = t_; }
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-      const int qt = item / HP, h = (item % HP) * 2 + a;
+      const AttnItem wi = attn_item(g, item, a);
+      const int qt = wi.qt, h = wi.h;
       const int ntok = g.group_ntok ? g.group_ntok[g.tile_group ? g.tile_group[qt] : 0] : g.ntok;
-      float l0 = 0.f, l1 = 0.f;
+      uint64_t l2 = 0ull;                                // packed (even columns, odd columns) row sums: one FADD2 per pair
       if constexpr (kTimers) tk0 = clock64();
+      // Every barrier round trip of these warps queues behind the MUFU instructions already in the SM's MIO pipe (the
+      // kernel's bottleneck): a wait costs ~450 clk even when the barrier completed long ago (instrumented: wait S 497,
+      // wait PV 482 clk per tile of 2840).  So the two MMA-completion barriers are PROBED in the middle of the
+      // exponentials — the probes travel in the shadow of that work — and the blocking waits run only if a probe failed.
+      bool s_ready = false;                              // S(j) already known complete
       for (int j = 0; j < nkv; ++j) {
-        mbar_wait(B.sfull(a), sfull_ph); sfull_ph ^= 1;
+        if (!s_ready) mbar_wait(B.sfull(a), sfull_ph);
+        sfull_ph ^= 1;
         fence_after_sync();
         HY3D_TICK(0)
         uint32_t sv[64];
@@ -237,21 +314,33 @@ __global__ void __launch_bounds__(ATT_FAST_THREADS, 1) k_attn_fast(AttnTC g) {
         if (lane == 0) mbar_arrive(B.sempty(a));       // S is in registers: the next S MMA may overwrite it
         HY3D_TICK(1)
         const int valid = ntok - j * 128 - hh * 64;    // columns >= valid are padding tokens (last tile of a ragged count)
-        if (valid < 64) {
+        bool pv_ok = j == 0, s_ok = false;
+        if (valid >= 64) {
 #pragma unroll
-          for (int i = 0; i < 64; ++i)
-            if (i >= valid) sv[i] = 0xff800000u;       // -inf -> p = 0
-        }
+          for (int i = 0; i < 32; ++i) {               // in place: sv[i] <- packed (p[2i], p[2i+1])
+            if (i == 20) {                             // probes: PV(j-1) consumed the previous P?  S(j+1) computed?
+              if (j > 0) pv_ok = mbar_test_wait(B.pvdone(a), pv_ph);
+              if (j + 1 < nkv) s_ok = mbar_test_wait(B.sfull(a), sfull_ph);
+            }
+            const float x0 = __uint_as_float(sv[2 * i]), x1 = __uint_as_float(sv[2 * i + 1]);
+            float p0, p1;
+            if (pair_on_fma<kPoly>(i)) exp2_poly2(x0, x1, p0, p1);
+            else { p0 = ex2(x0); p1 = ex2(x1); }
+            l2 = add_f2(l2, pack_f2(p0, p1));
+            sv[i] = pack_h2(p0, p1);
+          }
+        } else {                                       // ragged last tile: padding columns contribute p = 0
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {                 // in place: sv[i] <- packed (p[2i], p[2i+1])
-          const float x0 = __uint_as_float(sv[2 * i]), x1 = __uint_as_float(sv[2 * i + 1]);
-          const float p0 = exp_on_fma<kPoly>(2 * i) ? exp2_poly(x0) : ex2(x0);
-          const float p1 = exp_on_fma<kPoly>(2 * i + 1) ? exp2_poly(x1) : ex2(x1);
-          l0 += p0; l1 += p1;
-          sv[i] = pack_h2(p0, p1);
+          for (int i = 0; i < 32; ++i) {
+            const float p0 = 2 * i < valid ? ex2(__uint_as_float(sv[2 * i])) : 0.f;
+            const float p1 = 2 * i + 1 < valid ? ex2(__uint_as_float(sv[2 * i + 1])) : 0.f;
+            l2 = add_f2(l2, pack_f2(p0, p1));
+            sv[i] = pack_h2(p0, p1);
+          }
         }
         HY3D_TICK(2)
-        if (j > 0) { mbar_wait(B.pvdone(a), pv_ph); pv_ph ^= 1; }   // PV(j-1) has consumed the previous P
+        if (j > 0) { if (!pv_ok) mbar_wait(B.pvdone(a), pv_ph); pv_ph ^= 1; }   // PV(j-1) has consumed the previous P
+        s_ready = s_ok;
         HY3D_TICK(3)
         HY3D_TMEM_ST32(t_p, sv);
         tmem_wait_st();
@@ -262,7 +351,7 @@ __global__ void __launch_bounds__(ATT_FAST_THREADS, 1) k_attn_fast(AttnTC g) {
       }
       // ---- finalize: row sums of the two column halves through shared memory, O / l -> fp16 tile (q-tile, head) ----
       float* ls = lsum + a * 256;
-      ls[hh * 128 + r] = l0 + l1;
+      { float l0, l1; unpack_f2(l2, l0, l1); ls[hh * 128 + r] = l0 + l1; }
       asm volatile("bar.sync %0, 256;" ::"r"(1 + a) : "memory");
       const float inv = 1.f / (ls[r] + ls[128 + r]);
       mbar_wait(B.pvdone(a), pv_ph); pv_ph ^= 1;
@@ -275,7 +364,9 @@ __global__ void __launch_bounds__(ATT_FAST_THREADS, 1) k_attn_fast(AttnTC g) {
         float x[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(ov[i]) * inv;
-        if (g.split_out) {
+        if (!wi.store) {
+          // duplicate of the last query tile (odd tile count in share_kv mode): computed, not stored
+        } else if (g.split_out) {
 #pragma unroll
           for (int c16 = 0; c16 < 4; ++c16)
             store_t16_split(tile, tile + (size_t)g.H * TILE_BYTES, tile + (size_t)2 * g.H * TILE_BYTES, r, hh * 4 + c16, x + 8 * c16);
@@ -311,13 +402,13 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) k_attn_tc(AttnTC g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   AttnBars B;
-  const uint32_t tmem = attn_setup(smem, B, 4);
+  const uint32_t tmem = attn_setup(smem, B, 4, g.share_kv);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int HP = g.H / 2, nitems = g.Pb * HP, nkv = g.nkv;
+  const int nitems = attn_num_items(g), nkv = g.nkv;
 
   if (warp < 4) {
     reg_dealloc<80>();
-    if ((warp & 1) == 0) attn_producer(g, B, smem, warp >> 1);
+    if ((warp & 1) == 0) { if (!g.share_kv || warp == 0) attn_producer(g, B, smem, warp >> 1); }
     else attn_mma(g, B, smem, tmem, warp >> 1);
   } else {
     reg_alloc<200>();
@@ -329,7 +420,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) k_attn_tc(AttnTC g) {
     const uint32_t t_p = tmem + TM_P0 + a * 64 + ((uint32_t)(q * 32) << 16);
     uint32_t sfull_ph = 0, pv_ph = 0;
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-      const int qt = item / HP, h = (item % HP) * 2 + a;
+      const AttnItem wi = attn_item(g, item, a);
+      const int qt = wi.qt, h = wi.h;
       const int ntok = g.group_ntok ? g.group_ntok[g.tile_group ? g.tile_group[qt] : 0] : g.ntok;
       float m = -INFINITY, l = 0.f;
       for (int j = 0; j < nkv; ++j) {
@@ -411,7 +503,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) k_attn_tc(AttnTC g) {
         float x[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(ov[i]) * inv;
-        if (g.split_out) {
+        if (!wi.store) {
+        } else if (g.split_out) {
 #pragma unroll
           for (int c16 = 0; c16 < 4; ++c16)
             store_t16_split(tile, tile + (size_t)g.H * TILE_BYTES, tile + (size_t)2 * g.H * TILE_BYTES, r, c * 4 + c16, x + 8 * c16);

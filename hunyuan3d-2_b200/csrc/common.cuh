@@ -122,10 +122,15 @@ struct hy3d_ctx {
   DevBuf ws[12];                      // decoder workspaces
   DevBuf scratch, scratch2;           // octree / misc
   DevBuf ln_mr;                       // per-row (mean, rstd) of the LayerNorm folded into the running GEMM
-  void* pinned = nullptr;             // small pinned host buffer for read-backs
+  void* pinned = nullptr;             // small pinned host buffer for read-backs (4 KB; ints 128..135 = watchdog record)
   Prof prof;
+  // per-context launch state of the tcgen05 path (was function-local statics: one context per thread and device)
+  void* tmap_encode = nullptr;        // cuTensorMapEncodeTiled entry point
+  int l2_promo = -1;                  // HY3D_L2PROMO
+  int gemm_max_clusters[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // co-resident CTA pairs per GEMM epilogue variant
+  std::vector<float> axis_host;       // last per-axis coordinate tables uploaded to ws[11] (skips the upload when unchanged)
   // diagnostics: per-stage activations of the last decoded chunk (hy3d_debug_retain / hy3d_debug_fetch)
-  int attn_poly = 5;                  // share of the attention exponentials on the FMA pipe (HY3D_ATTN_POLY: 0 none, 1 = 2/16, 5 = 3/16, 2 = 4/16, 3 = 6/16, 4 = 8/16; bounded-score kernel)
+  int attn_poly = 2;                  // bounded-score attention kernel: PAIRS of every 8 pairs of exponentials evaluated as packed polynomials on the FMA pipe (HY3D_ATTN_POLY: 0 none, 1 = 2/16, 2 = 4/16 default, 3 = 6/16, 4 = 8/16; any other value = default)
   int debug_retain = 0;
   long long chunk_points = 262144;    // decoder chunk (HY3D_CHUNK; 131072 measured 1 % slower, 32768 7 % slower): activations of one chunk are what the stages hand over through L2 / HBM
   int xbits = 0;                      // HY3D_DBG: experiment bits for tools/gpu_chain_bench.py (results are garbage when set)
@@ -138,6 +143,12 @@ struct hy3d_ctx {
 int hy3d_debug_keep(hy3d_ctx* ctx, int stage, const void* src, size_t bytes, int layout, long long rows, int width);
 
 int hy3d_fail(hy3d_ctx* ctx, int code, const char* fmt, ...);
+// tcgen05 watchdog (tc_ptx.cuh): enqueue the read-back of the record before a stream synchronisation that happens anyway,
+// check it after — a barrier timeout inside a tensor kernel turns into an error of the next synchronising call.
+int hy3d_watchdog_enqueue(hy3d_ctx* ctx);
+int hy3d_watchdog_check(hy3d_ctx* ctx);
+// per-axis coordinate tables (n0 + n1 + n2 floats) resident in ws[11]; uploaded only when they changed
+int hy3d_upload_axes(hy3d_ctx* ctx, const float* h0, const float* h1, const float* h2, int n0, int n1, int n2);
 
 #define HY3D_CUDA(ctx, expr)                                                                   \
   do {                                                                                         \

@@ -722,22 +722,22 @@ __global__ void k_build_kv(const float* __restrict__ k32, const float* __restric
 int make_rows_map(hy3d_ctx* ctx, CUtensorMap* m, const void* base, uint64_t rows, int box_rows = 8) {
   typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-  static encode_fn encode = nullptr;
-  if (!encode) {
+  if (!ctx->tmap_encode) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult q;
     HY3D_CUDA(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
     if (!fn || q != cudaDriverEntryPointSuccess) return hy3d_fail(ctx, HY3D_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
-    encode = reinterpret_cast<encode_fn>(fn);
+    ctx->tmap_encode = fn;
   }
+  const encode_fn encode = reinterpret_cast<encode_fn>(ctx->tmap_encode);
   // `rows` counts 128-byte rows; the map itself uses rows of 256 x 8 bytes (2 KB): a 16 KB tile = box of 8 such rows, so the
   // TMA unit walks 8 long rows per tile instead of 128 short ones
   const cuuint64_t dims[2] = {256, rows / 16};
   const cuuint64_t strides[1] = {2048};
   const cuuint32_t box[2] = {256, (cuuint32_t)box_rows};     // 8 rows of 2 KB = one 16 KB tile (4 = half of it)
   const cuuint32_t estr[2] = {1, 1};
-  static int promo = -1;                       // HY3D_L2PROMO = 0 none, 1 64 B, 2 128 B, 3 256 B (default)
-  if (promo < 0) { const char* e = getenv("HY3D_L2PROMO"); promo = e ? atoi(e) : 3; }
+  if (ctx->l2_promo < 0) { const char* e = getenv("HY3D_L2PROMO"); ctx->l2_promo = e ? atoi(e) : 3; }   // 0 none, 1 64 B, 2 128 B, 3 256 B (default)
+  const int promo = ctx->l2_promo;
   const CUtensorMapL2promotion pr = promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
                                   : promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
   const CUresult r = encode(m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -759,7 +759,7 @@ __global__ void k_finish_stats(const float* __restrict__ st, int S, int n_p, flo
 template <int EPI>
 int launch_gemm(hy3d_ctx* ctx, const GemmTC& g, int fam) {
   HY3D_CUDA(ctx, cudaFuncSetAttribute(k_gemm_tc<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
-  static int max_clusters = 0;                                     // co-resident 2-CTA clusters (persistent grid)
+  int& max_clusters = ctx->gemm_max_clusters[EPI];                 // co-resident 2-CTA clusters (persistent grid)
   if (max_clusters == 0) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(ctx->num_sms / GEMM_CL * GEMM_CL); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = GEMM_SMEM;
@@ -795,7 +795,7 @@ int launch_gemm(hy3d_ctx* ctx, const GemmTC& g, int fam) {
 template <class K>
 int launch_attn_kernel(hy3d_ctx* ctx, K kern, const AttnTC& a, int threads) {
   HY3D_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
-  const int items = a.Pb * (a.H / 2);
+  const int items = a.share_kv ? ((a.Pb + 1) / 2) * a.H : a.Pb * (a.H / 2);
   const int grid = items < ctx->num_sms ? items : ctx->num_sms;
   kern<<<grid, threads, ATT_SMEM, ctx->stream>>>(a);
   return 0;
@@ -803,21 +803,22 @@ int launch_attn_kernel(hy3d_ctx* ctx, K kern, const AttnTC& a, int threads) {
 int launch_attn(hy3d_ctx* ctx, AttnTC a, bool fast, int fam) {
   HY3D_PROF(ctx, fam);
   if (ctx->xbits & 0x20) fast = false;
+  // one K/V set for all query tiles (no per-tile KV groups): pairs of query tiles share every K/V tile they stream
+  a.share_kv = (a.tile_group == nullptr && !(ctx->xbits & 0x100)) ? 1 : 0;
   int rc = 0;
   if (fast) {
     if (ctx->xbits & 0x40) {
       void* tm = nullptr;
       HY3D_CUDA(ctx, cudaGetSymbolAddress(&tm, hy3d_tm));
       a.timers = reinterpret_cast<unsigned long long*>(tm);
-      rc = launch_attn_kernel(ctx, k_attn_fast<0, true>, a, ATT_FAST_THREADS);
+      rc = launch_attn_kernel(ctx, k_attn_fast<2, true>, a, ATT_FAST_THREADS);
     } else {
-      switch (ctx->attn_poly) {
+      switch (ctx->attn_poly) {            // pairs of every 8 whose exponentials run as packed polynomials on the FMA pipe
+        case 0: rc = launch_attn_kernel(ctx, k_attn_fast<0, false>, a, ATT_FAST_THREADS); break;
         case 1: rc = launch_attn_kernel(ctx, k_attn_fast<1, false>, a, ATT_FAST_THREADS); break;
-        case 2: rc = launch_attn_kernel(ctx, k_attn_fast<2, false>, a, ATT_FAST_THREADS); break;
         case 3: rc = launch_attn_kernel(ctx, k_attn_fast<3, false>, a, ATT_FAST_THREADS); break;
         case 4: rc = launch_attn_kernel(ctx, k_attn_fast<4, false>, a, ATT_FAST_THREADS); break;
-        case 5: rc = launch_attn_kernel(ctx, k_attn_fast<5, false>, a, ATT_FAST_THREADS); break;
-        default: rc = launch_attn_kernel(ctx, k_attn_fast<0, false>, a, ATT_FAST_THREADS); break;
+        default: rc = launch_attn_kernel(ctx, k_attn_fast<2, false>, a, ATT_FAST_THREADS); break;
       }
     }
   } else {
@@ -1347,6 +1348,22 @@ extern "C" int hy3d_debug_timers(hy3d_ctx* ctx, uint64_t h_out[32]) {
   unsigned long long zero[32] = {};
   HY3D_CUDA(ctx, cudaMemcpyToSymbol(hy3d_tm, zero, sizeof(zero)));
   return HY3D_OK;
+}
+
+int hy3d_watchdog_enqueue(hy3d_ctx* ctx) {
+  int* rec = reinterpret_cast<int*>(ctx->pinned) + 128;
+  HY3D_CUDA(ctx, cudaMemcpyFromSymbolAsync(rec, hy3d_wd, sizeof(int) * 8, 0, cudaMemcpyDeviceToHost, ctx->stream));
+  return 0;
+}
+
+int hy3d_watchdog_check(hy3d_ctx* ctx) {
+  const int* rec = reinterpret_cast<const int*>(ctx->pinned) + 128;
+  if (!rec[0]) return 0;
+  const int blk = rec[1], thr = rec[2], bar = rec[3], par = rec[4];
+  int zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  cudaMemcpyToSymbol(hy3d_wd, zero, sizeof(zero));
+  return hy3d_fail(ctx, HY3D_ERR_STATE, "tcgen05 kernel barrier timeout (block %d thread %d barrier 0x%x parity %d): the results of the "
+                   "decoder launches before this call are invalid", blk, thr, bar, par);
 }
 
 extern "C" int hy3d_debug_watchdog(hy3d_ctx* ctx, int32_t h_out[8]) {

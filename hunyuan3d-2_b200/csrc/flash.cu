@@ -208,14 +208,7 @@ int make_source(hy3d_ctx* ctx, const hy3d_coords* c, const int32_t* d_index, int
   } else if (c->mode == 3) {
     if (!c->axis0 || !c->axis1 || !c->axis2) return hy3d_fail(ctx, HY3D_ERR_ARG, "axis tables missing");
     s.mode = 3;
-    size_t na = (size_t)n0 + n1 + n2;
-    HY3D_CUDA(ctx, ctx->ws[11].reserve(na * sizeof(float)));
-    std::vector<float> tab(na);
-    memcpy(tab.data(), c->axis0, n0 * sizeof(float));
-    memcpy(tab.data() + n0, c->axis1, n1 * sizeof(float));
-    memcpy(tab.data() + n0 + n1, c->axis2, n2 * sizeof(float));
-    HY3D_CUDA(ctx, cudaMemcpyAsync(ctx->ws[11].p, tab.data(), na * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    HY3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (int rc = hy3d_upload_axes(ctx, c->axis0, c->axis1, c->axis2, n0, n1, n2)) return rc;
     s.axis = ctx->ws[11].as<float>();
   } else {
     return hy3d_fail(ctx, HY3D_ERR_ARG, "coords.mode must be 2 (idx*cell+bmin) or 3 (axis tables)");

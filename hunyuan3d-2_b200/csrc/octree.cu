@@ -225,9 +225,10 @@ int hy3d_refine_level(hy3d_ctx* ctx, const float* d_coarse, int32_t n, int32_t n
   }
   long long* pinned = reinterpret_cast<long long*>(ctx->pinned);
   HY3D_CUDA(ctx, cudaMemcpyAsync(pinned, blockoff + nblocks, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+  if (int rc = hy3d_watchdog_enqueue(ctx)) return rc;
   HY3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   *h_count = pinned[0];
-  return HY3D_OK;
+  return hy3d_watchdog_check(ctx);        // the coarse grid came from the tensor kernels: a barrier timeout there invalidates it
 }
 
 int hy3d_fill(hy3d_ctx* ctx, float* d_grid, int64_t n, float value) {

@@ -69,13 +69,22 @@ class B200ShapeVAE:
     def forward(self, latents: torch.Tensor, dtype=torch.float32, impl: str = None) -> torch.Tensor:
         """ShapeVAE.forward (reference model.py:186-189): post_kl + Transformer.
 
-        impl='tc' (default where the shapes allow): hand-written tcgen05 kernels of libhy3dgeo.so
+        impl='tc' (the default and the product path): hand-written tcgen05 kernels of libhy3dgeo.so
         (``hy3d_transformer_forward``: 3-term split fp16 GEMMs = fp32-grade, LayerNorms folded, fp16
-        self-attention), float32 result.  impl='torch': cuBLAS + SDPA library ops in ``dtype``
-        (kept for odd shapes and as a cross-check; 47 ms in fp32 for 3072 tokens vs ~5 ms)."""
+        self-attention), float32 result.  Shapes those kernels do not tile (head dim != 64, width not a multiple
+        of 256, token count not a multiple of 128) raise — there is no silent library fallback.
+        impl='torch' must be asked for explicitly: the same network on cuBLAS + SDPA library ops in ``dtype``, kept
+        as a cross-check for the parity tests (47 ms in fp32 for 3072 tokens vs ~5 ms)."""
         if impl is None:
-            impl = "tc" if self._tc_ok(latents) else "torch"
+            impl = "tc"
+        if impl not in ("tc", "torch"):
+            raise ValueError(f"impl must be 'tc' or 'torch', got {impl!r}")
         if impl == "tc":
+            if not self._tc_ok(latents):
+                raise RuntimeError(
+                    "B200ShapeVAE.forward: the tcgen05 latent transformer needs head_dim 64, width % 256 == 0, embed_dim % 64 == 0 "
+                    f"and a token count that is a multiple of 128 (got width {self.cfg.width}, heads {self.cfg.heads}, embed_dim "
+                    f"{self.cfg.embed_dim}, tokens {latents.shape[-2]}); pass impl='torch' explicitly for the library statement")
             from ._lib import get_context
             ctx = get_context(self.device)
             ctx.set_transformer(self.sd, self.cfg, key=id(self.sd), owner=self)

@@ -69,10 +69,28 @@ class MCSurfaceExtractor(SurfaceExtractor):
     """``skimage.measure.marching_cubes(vol, mc_level, method="lewiner")`` + rescale
     (reference :68-76) as device kernels: classify -> count -> emit, welded vertices,
     ``v / (res+1) * bbox_size + bbox_min`` evaluated in float64 on the device.  Only the
-    mesh crosses PCIe (the reference copies the whole fp32 grid to the host, :70)."""
+    mesh crosses PCIe (the reference copies the whole fp32 grid to the host, :70).
+
+    The marching cubes here is the classic 256-case table with one fixed sign rule for ambiguous faces, vertices in
+    lexicographic (voxel, axis) order — NOT scikit-image's Lewiner variant (no face / interior tests, different vertex and
+    face order): same surface up to the ambiguous-cube topology and the indexing, see INTEGRATION.md "marching cubes".
+
+    ``cull_nonfinite`` (default off = the reference's output, NaN vertices included): drop, on the device, the NaN / inf
+    vertices the sparse decoders produce along the rim of their visited band, the faces that use them and any vertex left
+    unreferenced — what ``trimesh.Trimesh(...)`` does on the host in the reference's next step (``export_to_trimesh``,
+    pipelines.py:95-110), which then finds nothing to remove.  ``hy3dgeo.export_to_trimesh`` does cull + winding flip."""
+
+    def __init__(self, cull_nonfinite: bool = False):
+        self.cull_nonfinite = cull_nonfinite
 
     def run_device(self, grid_logit: torch.Tensor, *, mc_level, bounds, octree_resolution, **kwargs):
         """Returns device tensors (verts float32 [V,3], faces int32 [F,3])."""
+        res = self._extract_device(grid_logit, mc_level=mc_level, bounds=bounds, octree_resolution=octree_resolution, **kwargs)
+        if res is not None and self.cull_nonfinite:
+            res = get_context(res[0].device).mesh_clean(res[0], res[1], flip_winding=False)
+        return res
+
+    def _extract_device(self, grid_logit: torch.Tensor, *, mc_level, bounds, octree_resolution, **kwargs):
         if type(grid_logit).__name__ == "SlabGrid":
             return self.run_sharded(grid_logit, mc_level=mc_level, bounds=bounds, octree_resolution=octree_resolution, **kwargs)
         if not isinstance(grid_logit, torch.Tensor) or not grid_logit.is_cuda:
@@ -137,6 +155,26 @@ class DMCSurfaceExtractor(SurfaceExtractor):
 
     def run(self, grid_logit, *, octree_resolution, **kwargs):
         raise ImportError("DMCSurfaceExtractor is not provided by hy3dgeo; set mc_algo to 'mc'")
+
+
+def export_to_trimesh(mesh_output, device=None):
+    """``export_to_trimesh`` of the reference (hy3dgen/shapegen/pipelines.py:95-110) with the mesh clean-up done on the GPU:
+    winding flipped (``mesh_f[:, ::-1]``), non-finite vertices, the faces that reference them and unreferenced vertices
+    removed (what ``trimesh.Trimesh(v, f)``'s default processing does).  Accepts one ``Latent2MeshOutput`` or a list (``None``
+    items pass through).  Returns ``trimesh.Trimesh(..., process=False)`` objects when trimesh is importable, otherwise
+    ``Latent2MeshOutput`` objects holding the cleaned, flipped arrays."""
+    if isinstance(mesh_output, list):
+        return [None if m is None else export_to_trimesh(m, device) for m in mesh_output]
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    ctx = get_context(dev)
+    v = torch.from_numpy(np.ascontiguousarray(mesh_output.mesh_v, dtype=np.float32)).to(dev, non_blocking=True)
+    f = torch.from_numpy(np.ascontiguousarray(mesh_output.mesh_f, dtype=np.int32)).to(dev, non_blocking=True)
+    vo, fo = _to_host(*ctx.mesh_clean(v, f, flip_winding=True))
+    try:
+        import trimesh
+    except ImportError:
+        return Latent2MeshOutput(mesh_v=vo, mesh_f=fo)
+    return trimesh.Trimesh(vo, fo, process=False)
 
 
 SurfaceExtractors = {

@@ -66,26 +66,30 @@ def flash_levels(octree_resolution: int, min_resolution: int = 63, mini_grid_num
     return res
 
 
-def _decoder_identity(geo_decoder):
-    """(state_dict, config, cache key) of a CrossAttentionDecoder-like object."""
+def _decoder_key(geo_decoder):
+    """(state_dict, cache key) of a CrossAttentionDecoder-like object — no device synchronisation: the key is the
+    module's identity plus every tensor's storage address and in-place version counter.  (Edits made through
+    ``param.data`` do not bump the counter: call ``hy3dgeo._lib.get_context(device).invalidate_weights()`` after such
+    an edit.)"""
     if not (hasattr(geo_decoder, "state_dict") and hasattr(geo_decoder, "fourier_embedder")
             and hasattr(geo_decoder, "cross_attn_decoder")):
         raise TypeError(
             "geo_decoder must be a CrossAttentionDecoder (its weights are read and run by the CUDA kernels); "
             f"got {type(geo_decoder).__name__}. hy3dgeo has no CPU/eager fallback for arbitrary callables.")
     sd = geo_decoder.state_dict()
-    cfg = W.config_from_geo_decoder(geo_decoder)
     key = (id(geo_decoder),) + tuple((k, v.data_ptr(), getattr(v, "_version", 0)) for k, v in sd.items())
-    return sd, cfg, key
+    return sd, key
 
 
 def bind(latents: torch.Tensor, geo_decoder) -> GeoContext:
-    """Context of the latents' device with this decoder's weights resident."""
+    """Context of the latents' device with this decoder's weights resident.  The hyper-parameters are read (one small
+    device->host copy of the Fourier frequencies) only when the weights are not already cached."""
     if not latents.is_cuda:
         raise RuntimeError("latents must live on a CUDA device (hy3dgeo has no CPU path)")
     ctx = get_context(latents.device)
-    sd, cfg, key = _decoder_identity(geo_decoder)
-    ctx.set_decoder(sd, cfg, key, owner=geo_decoder)
+    sd, key = _decoder_key(geo_decoder)
+    if not ctx.has_decoder(key, geo_decoder):
+        ctx.set_decoder(sd, W.config_from_geo_decoder(geo_decoder), key, owner=geo_decoder)
     return ctx
 
 

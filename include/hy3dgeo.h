@@ -201,6 +201,14 @@ int hy3d_mc_count_slab(hy3d_ctx* ctx, const float* d_grid, int32_t n0, int32_t n
                        int64_t* h_num_verts, int64_t* h_num_faces, float h_minmax[3]);
 int hy3d_mc_emit_slab(hy3d_ctx* ctx, const double h_div[3], const double h_mul[3], const double h_add[3], int32_t plane0,
                       int64_t id_base, float* d_verts, int32_t* d_faces);
+/* ---- mesh clean-up: the device side of export_to_trimesh (hy3dgen/shapegen/pipelines.py:95-110) ---------------------
+ * `mesh_f[:, ::-1]` (flip_winding != 0) and what trimesh.Trimesh(v, f)'s default processing does to a mesh with
+ * non-finite vertices: faces that reference a NaN / inf vertex are dropped, then vertices that are non-finite or no longer
+ * referenced, and the faces are re-indexed; the order of the survivors is preserved.  d_verts fp32 [nV,3], d_faces int32
+ * [nF,3]; the outputs need room for nV / nF entries and must not alias the inputs.  Returns the new counts in HOST
+ * variables (synchronises the stream once). */
+int hy3d_mesh_clean(hy3d_ctx* ctx, const float* d_verts, int64_t nV, const int32_t* d_faces, int64_t nF, int32_t flip_winding,
+                    float* d_verts_out, int32_t* d_faces_out, int64_t* h_num_verts_out, int64_t* h_num_faces_out);
 /* Table-independent classification for parity tests: 8-bit case per cube, [n0-1,n1-1,n2-1]. */
 int hy3d_mc_cases(hy3d_ctx* ctx, const float* d_grid, int32_t n0, int32_t n1, int32_t n2, float level,
                   uint8_t* d_cases);
@@ -227,9 +235,10 @@ int hy3d_debug_retain(hy3d_ctx* ctx, int enable);
  * (1 GEMM epilogue, 2 GEMM MMAs, 4 GEMM epilogue stores) so that their cost can be measured by difference — results
  * are garbage while those are set; 0x20 forces the online-softmax attention kernel, 0x40 runs the instrumented
  * bounded-score attention kernel (hy3d_debug_timers), 0x10000 the CUDA-core K/V projection (results stay valid);
- * `attn_poly` = share of the attention exponentials evaluated on the FMA pipe (0 none, 1 = 2/16, 5 = 3/16, 2 = 4/16,
- * 3 = 6/16, 4 = 8/16).
- * Defaults (0, 5) are the product configuration. */
+ * 0x100 gives every attention stream its own K/V ring even when all query tiles share one K/V set;
+ * `attn_poly` = pairs of every 8 pairs of attention exponentials evaluated as packed polynomials on the FMA pipe
+ * (0 none, 1 = 2/16, 2 = 4/16, 3 = 6/16, 4 = 8/16; other values select the default, 2).
+ * Defaults (0, 2) are the product configuration. */
 int hy3d_debug_experiment(hy3d_ctx* ctx, int bits, int attn_poly);
 /* Phase clocks accumulated by the instrumented attention kernel (experiment bit 0x40), returned and cleared:
  * per head stream a (0, 1) h_out[8a + i] = SM cycles one softmax thread of CTA 0 spent in phase i

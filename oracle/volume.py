@@ -206,6 +206,35 @@ def flash_pack_bins(bin_ids: Sequence[int], counts: Sequence[int], num_chunks: i
     return calls
 
 
+def flashvdm_level(decode_group: Callable, grid: np.ndarray, bounds, r: int, last: bool, num_chunks: int = 10000,
+                   mc_level: float = 0.0):
+    """One refined level of vd:373-431: ``grid`` is the previous level (sentinel -10000 = unvisited) -> the level of
+    resolution ``r`` in the same form, the number of queries and the per-call (bin ids, counts).  Exposed on its own so
+    that a device implementation can be checked level by level on ITS OWN previous level: the active set, the 6^3
+    binning and the stride sampling are discontinuous in the coarse values, so two implementations whose logits differ
+    below tolerance may legitimately diverge after a threshold flip — but never given the same field."""
+    up = refine_active_set(grid, mc_level, last=last)
+    idx = np.stack(np.nonzero(up), axis=1)
+    P = refined_coords(idx, bounds, r)
+    bins = flash_bins(P)
+    order_ = np.argsort(bins, kind="stable")               # vd:404 (stable on CPU, SURVEY §7.3-5)
+    Ps = P[order_]
+    ub, uc = np.unique(bins, return_counts=True)
+    calls = flash_pack_bins(ub.tolist(), uc.tolist(), num_chunks)
+    vals_sorted = np.empty(Ps.shape[0], dtype=np.float32)
+    start = 0
+    for ids, cnts in calls:
+        n = int(sum(cnts))
+        out = decode_group(torch.from_numpy(Ps[None, start:start + n]), (ids, cnts)).numpy()
+        vals_sorted[start:start + n] = out.reshape(-1)
+        start += n
+    vals = np.empty_like(vals_sorted)
+    vals[order_] = vals_sorted
+    nxt = np.full(up.shape, SENTINEL, dtype=np.float32)
+    nxt[up] = vals
+    return nxt, int(idx.shape[0]), calls
+
+
 def flashvdm_decode(decode_group: Callable, bounds=1.01, num_chunks=10000, mc_level=0.0,
                     octree_resolution=None, min_resolution=63, mini_grid_num=4, return_stats=False):
     """vd:291-435 for one latent -> float32 [N',N',N'], NaN = unvisited.
@@ -228,27 +257,8 @@ def flashvdm_decode(decode_group: Callable, bounds=1.01, num_chunks=10000, mc_le
     grid = flat.reshape(N0, N0, N0)
     stats = {"levels": levels, "queries": [N0 ** 3], "calls": []}
     for r in levels[1:]:
-        up = refine_active_set(grid, mc_level, last=(r == levels[-1]))
-        idx = np.stack(np.nonzero(up), axis=1)
-        P = refined_coords(idx, bounds, r)
-        bins = flash_bins(P)
-        order_ = np.argsort(bins, kind="stable")               # vd:404 (stable on CPU)
-        Ps = P[order_]
-        ub, uc = np.unique(bins, return_counts=True)
-        calls = flash_pack_bins(ub.tolist(), uc.tolist(), num_chunks)
-        vals_sorted = np.empty(Ps.shape[0], dtype=np.float32)
-        start = 0
-        for ids, cnts in calls:
-            n = int(sum(cnts))
-            out = decode_group(torch.from_numpy(Ps[None, start:start + n]), (ids, cnts)).numpy()
-            vals_sorted[start:start + n] = out.reshape(-1)
-            start += n
-        vals = np.empty_like(vals_sorted)
-        vals[order_] = vals_sorted
-        nxt = np.full(up.shape, SENTINEL, dtype=np.float32)
-        nxt[up] = vals
-        grid = nxt
-        stats["queries"].append(int(idx.shape[0]))
+        grid, nq, calls = flashvdm_level(decode_group, grid, bounds, r, r == levels[-1], num_chunks, mc_level)
+        stats["queries"].append(nq)
         stats["calls"].append([(list(i), list(c)) for i, c in calls])
     grid = grid.copy()
     grid[grid == SENTINEL] = np.nan

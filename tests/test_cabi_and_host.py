@@ -78,9 +78,9 @@ def test_interface_mirrors_reference():
 
 
 def test_type_error_for_arbitrary_callable():
-    from hy3dgeo.volume_decoders import _decoder_identity
+    from hy3dgeo.volume_decoders import _decoder_key
     with pytest.raises(TypeError):
-        _decoder_identity(lambda queries, latents: None)
+        _decoder_key(lambda queries, latents: None)
 
 
 def test_synthetic_state_dict_keys_and_config_roundtrip():

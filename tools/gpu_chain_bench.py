@@ -85,5 +85,7 @@ for bits in [int(b) for b in args.bits.split(",")]:
         if bits & 0x40:
             tm = ctx.debug_timers()
             res["softmax_clk_per_tile"] = [[round(tm[8 * a + i] / max(tm[8 * a + 7], 1)) for i in range(6)] for a in range(2)]
+            # MMA warp of each stream: cycles per KV tile waiting for the K tile, the S buffer, the V tile, the stored P
+            res["mma_wait_clk_per_tile"] = [[round(tm[16 + 4 * a + i] / max(tm[8 * a + 7], 1)) for i in range(4)] for a in range(2)]
         print(json.dumps(res), flush=True)
 ctx.debug_experiment(0, 5)

@@ -8,6 +8,22 @@ __global__ void k(float* out, int iters, float seed) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) a[i] = seed + threadIdx.x * 1e-3f + i;
   unsigned pk = 0;
+  if (OP == 6 || OP == 7) {                       // packed f32x2: the pairs stay in 64-bit registers for the whole loop
+    unsigned long long v[8], sd;
+    asm volatile("mov.b64 %0, {%1, %1};" : "=l"(sd) : "f"(seed));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) asm volatile("mov.b64 %0, {%1, %2};" : "=l"(v[i]) : "f"(a[i]), "f"(a[(i + 1) & 7]));
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (OP == 6) asm volatile("fma.rn.f32x2 %0, %0, %1, %1;" : "+l"(v[i]) : "l"(sd));
+        if (OP == 7) asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(v[i]) : "l"(sd));
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { float x, y; asm volatile("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v[i])); a[i] = x + y; }
+    iters = 0;
+  }
   for (int it = 0; it < iters; ++it) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -42,5 +58,6 @@ void run(const char* name, int opsPerIter) {
 }
 int main() {
   run<0>("MUFU.EX2", 1); run<1>("FADD", 1); run<2>("FFMA", 1); run<3>("F2FP", 1); run<4>("FMNMX3", 1); run<5>("EX2+2FADD", 3);
+  run<6>("FFMA2(x2)", 2); run<7>("FADD2(x2)", 2);
   return 0;
 }
