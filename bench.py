@@ -132,7 +132,7 @@ def main():
                     help="hier: BASELINE configs[2] (Hierarchical, the metric's configuration); dense: configs[1] / configs[4] (Vanilla)")
     ap.add_argument("--res", type=int, default=None, help="octree resolution (default 384 for hier, 256 for dense)")
     ap.add_argument("--model", default="full", choices=["full", "mini"])
-    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline sample length; 0 skips the CPU leg (tuning runs)")
     ap.add_argument("--gather", action="store_true", help="N > 1: gather the grid instead of keeping it sharded through marching cubes")
     args = ap.parse_args()
     res = args.res if args.res is not None else (384 if args.config == "hier" else 256)
@@ -300,7 +300,7 @@ def main():
         pass
     chain_ms = sum(fams[k][0] for k in fams if k in fl or k in ("layernorm", "embed"))
     all_tf = sum(fl.values()) * pts_local * prof_steps / (chain_ms / 1e3) / 1e12
-    bound, akern = ctx.attention_info()
+    bound, akern, mbound = ctx.attention_info()
     roofline = {"bound": "tensor", "kernel": top, "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                 "traffic": traffic, "peak_source": peak_src, "launches": top_cnt, "avg_launch_ms": top_ms / max(top_cnt, 1),
                 "flops_per_point": fl[top], "share_of_step": top_ms / total_fam_ms,
@@ -311,7 +311,7 @@ def main():
             "dtype": "f16 operands, f32 accumulate", "data": "synthetic", "config": config,
             "latents2mesh_ms": ms / args.steps, "queries": total_q, "queries_per_level": queries,
             "visited_fraction": queries[-1] / N ** 3, "mesh": {"vertices": mesh_size[0], "faces": mesh_size[1]},
-            "attention_kernel": akern, "attention_score_bound": bound,
+            "attention_kernel": akern, "attention_score_bound": {"from_norm_weights": bound, "measured_max_k_norm": mbound},
             "roofline": roofline}
     # ---- HBM-bound passes, whole-pass fractions (SURVEY §8d algorithmic bytes), rank 0's share
     if hier and "octree" in fams and world == 1:
@@ -335,7 +335,7 @@ def main():
                    "h2d_bytes_per_step": z_host.numel() * z_host.element_size(), "d2h_bytes_per_step": mesh_bytes[0]}
     line["gpu_launches"] = launches
     line["clocks"] = clocks
-    if world == 1:
+    if world == 1 and args.cpu_seconds > 0:
         lat_cpu, tf_s = cpu_port_setup(cfg, sd, W.synthetic_latents(cfg, 1, 1234))
         rate, chunks, threads = cpu_port_rate(cfg, sd, lat_cpu, args.cpu_seconds, res=levels[0])
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",

@@ -64,7 +64,7 @@ SYMBOLS = {
     "hy3d_last_error": (C.c_char_p, [C.c_void_p]),
     "hy3d_set_precision": (C.c_int, [C.c_void_p, C.c_int]),
     "hy3d_launch_count": (C.c_int64, [C.c_void_p]),
-    "hy3d_attention_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
+    "hy3d_attention_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_float)]),
     "hy3d_set_decoder_weights": (C.c_int, [C.c_void_p, C.POINTER(DecoderDesc)]),
     "hy3d_set_transformer_weights": (C.c_int, [C.c_void_p, C.POINTER(TransformerDesc)]),
     "hy3d_transformer_forward": (C.c_int, [C.c_void_p, c_f32p, C.c_int32, c_f32p]),
@@ -103,6 +103,7 @@ SYMBOLS = {
     "hy3d_debug_retain": (C.c_int, [C.c_void_p, C.c_int]),
     "hy3d_debug_experiment": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "hy3d_debug_timers": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    "hy3d_debug_attn_redo": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
     "hy3d_debug_fetch": (C.c_int, [C.c_void_p, C.c_int, c_f32p, C.c_int64, C.POINTER(C.c_int32)]),
     "hy3d_mc_cases": (C.c_int, [C.c_void_p, c_f32p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p]),
 }
@@ -183,10 +184,10 @@ class GeoContext:
         return int(self.lib.hy3d_launch_count(self.h))
 
     def attention_info(self):
-        """(score bound, 'bounded-score' | 'online-softmax') of the decoder weights currently loaded."""
-        b, f = C.c_float(), C.c_int32()
-        self._check(self.lib.hy3d_attention_info(self.h, C.byref(b), C.byref(f)), "hy3d_attention_info")
-        return float(b.value), ("bounded-score" if f.value else "online-softmax")
+        """(weight-only score bound, kernel name, measured score bound of the current K/V) of the decoder currently loaded."""
+        b, f, m = C.c_float(), C.c_int32(), C.c_float()
+        self._check(self.lib.hy3d_attention_info(self.h, C.byref(b), C.byref(f), C.byref(m)), "hy3d_attention_info")
+        return float(b.value), ["online-softmax", "bounded-score", "bounded-score + per-head shift + exact redo"][f.value], float(m.value)
 
     @staticmethod
     def _same_owner(ref, owner) -> bool:
@@ -349,6 +350,11 @@ class GeoContext:
         out = (C.c_uint64 * 32)()
         self._check(self.lib.hy3d_debug_timers(self.h, out), "hy3d_debug_timers")
         return list(out)
+
+    def debug_attn_redo(self) -> int:
+        n = C.c_int32()
+        self._check(self.lib.hy3d_debug_attn_redo(self.h, C.byref(n)), "hy3d_debug_attn_redo")
+        return int(n.value)
 
     def debug_retain(self, enable: bool):
         self._check(self.lib.hy3d_debug_retain(self.h, int(enable)), "hy3d_debug_retain")

@@ -146,6 +146,7 @@ void hy3d_destroy(hy3d_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   ctx->w.f32.release(); ctx->w.tc.release();
   ctx->kv.k32.release(); ctx->kv.v32.release(); ctx->kv.ktile.release(); ctx->kv.vtile.release();
+  ctx->kv.head_shift.release(); ctx->kv.redo.release();
   ctx->mc.bits.release(); ctx->mc.rowcnt.release(); ctx->mc.rowoff.release(); ctx->mc.stats.release();
   for (auto& b : ctx->ws) b.release();
   { TransformerState& t = ctx->tf; for (DevBuf* b : {&t.tc, &t.f32, &t.x, &t.ta, &t.tq, &t.to, &t.th, &t.kt, &t.vt, &t.st, &t.tz}) b->release(); }
@@ -177,10 +178,34 @@ int hy3d_set_precision(hy3d_ctx* ctx, int precision) {
 
 int64_t hy3d_launch_count(const hy3d_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
-int hy3d_attention_info(const hy3d_ctx* ctx, float* h_score_bound, int32_t* h_bounded_kernel) {
+int hy3d_attention_info(hy3d_ctx* ctx, float* h_score_bound, int32_t* h_bounded_kernel, float* h_measured_bound) {
   if (!ctx || !h_score_bound || !h_bounded_kernel) return HY3D_ERR_ARG;
   *h_score_bound = ctx->w.attn_bound;
-  *h_bounded_kernel = (ctx->w.attn_fast && !(ctx->xbits & 0x20)) ? 1 : 0;
+  const bool fast = ctx->w.attn_fast && !(ctx->xbits & 0x20);
+  *h_bounded_kernel = !fast ? 0 : (ctx->kv.shifted ? 2 : 1);
+  if (h_measured_bound) {
+    *h_measured_bound = ctx->w.attn_bound;
+    if (ctx->w.attn_fast && ctx->kv.ready && ctx->kv.head_shift.p) {        // largest per-head bound of the current latent set
+      const int H = ctx->w.H;
+      std::vector<float> b(2 * (size_t)H);
+      HY3D_CUDA(ctx, cudaSetDevice(ctx->device));
+      HY3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      HY3D_CUDA(ctx, cudaMemcpy(b.data(), ctx->kv.head_shift.p, b.size() * sizeof(float), cudaMemcpyDeviceToHost));
+      float mx = 0.f;
+      for (int h = 0; h < H; ++h) mx = b[H + h] > mx ? b[H + h] : mx;
+      *h_measured_bound = mx;
+    }
+  }
+  return HY3D_OK;
+}
+
+int hy3d_debug_attn_redo(hy3d_ctx* ctx, int32_t* h_items) {
+  if (!ctx || !h_items) return HY3D_ERR_ARG;
+  *h_items = 0;
+  if (!ctx->kv.redo.p) return HY3D_OK;
+  HY3D_CUDA(ctx, cudaSetDevice(ctx->device));
+  HY3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  HY3D_CUDA(ctx, cudaMemcpy(h_items, ctx->kv.redo.p, sizeof(int32_t), cudaMemcpyDeviceToHost));
   return HY3D_OK;
 }
 

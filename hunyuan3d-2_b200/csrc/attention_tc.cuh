@@ -52,6 +52,12 @@ struct AttnTC {
   int Pb, H, nkv, ntok;  // nkv = tiles per (group, head); ntok = valid tokens when group_ntok == null
   int split_out;         // O written as [hi | lo | hi] over 3H k-blocks (operand of a 3-term split GEMM)
   int share_kv;          // 1: streams = two query tiles of one head sharing every K/V tile; 0: two heads of one query tile
+  // bounded-score kernel with measured bounds: p = exp2(s - head_shift[h]); rows whose sum falls below ntok * 2^-14 (all their
+  // scores far below the head's bound: the fp16 probabilities would be subnormal) flag their (tile, head pair) for an exact redo
+  const float* head_shift;      // [H] or null (no shift)
+  int* redo_count; int* redo_list; int* redo_flag;      // device work list filled by the bounded-score kernel (or null)
+  // online-softmax kernel in list mode: items come from a device work list written by an earlier launch
+  const int* work_count; const int* work_list;
   unsigned long long* timers;   // k_attn_fast<.., true>: phase clocks of CTA 0 (see hy3d_debug_timers)
 };
 
@@ -98,10 +104,16 @@ __device__ __forceinline__ uint32_t attn_setup(uint8_t* smem, AttnBars& B, int s
 // Work item -> (query tile, head) of stream a.  share_kv: item = (pair of query tiles, head), stream a takes tile 2 pair + a
 // (an odd tile count leaves the last pair's second stream on a duplicate of the last tile; it computes but does not store).
 struct AttnItem { int qt, h; bool store; };
-__device__ __forceinline__ int attn_num_items(const AttnTC& g) { return g.share_kv ? ((g.Pb + 1) >> 1) * g.H : g.Pb * (g.H >> 1); }
+__device__ __forceinline__ int attn_num_items(const AttnTC& g) {
+  if (g.work_count) return *g.work_count;           // list mode (uniform: every thread reads the same word)
+  return g.share_kv ? ((g.Pb + 1) >> 1) * g.H : g.Pb * (g.H >> 1);
+}
 __device__ __forceinline__ AttnItem attn_item(const AttnTC& g, int item, int a) {
   AttnItem it;
-  if (g.share_kv) {
+  if (g.work_list) {                                // entry = query tile * (H / 2) + head pair
+    const int HP = g.H >> 1, e = g.work_list[item];
+    it.qt = e / HP; it.h = (e - it.qt * HP) * 2 + a; it.store = true;
+  } else if (g.share_kv) {
     const int pr = item / g.H, q = 2 * pr + a;
     it.h = item - pr * g.H; it.store = q < g.Pb; it.qt = it.store ? q : g.Pb - 1;
   } else {
@@ -240,7 +252,8 @@ __device__ __forceinline__ bool exp_on_fma(int i) {
 // f32x2 instructions (FADD2 / FFMA2: both lanes for one issue slot) — kPairs of every 8 pairs (= 2 kPairs / 16 elements).
 template <int kPairs>
 __device__ __forceinline__ bool pair_on_fma(int pair) {
-  constexpr unsigned kMask = kPairs <= 0 ? 0x00u : kPairs == 1 ? 0x10u : kPairs == 2 ? 0x44u : kPairs == 3 ? 0x54u : 0xAAu;
+  constexpr unsigned kMask = kPairs <= 0 ? 0x00u : kPairs == 1 ? 0x10u : kPairs == 2 ? 0x44u : kPairs == 3 ? 0x54u : kPairs == 4 ? 0xAAu
+                           : kPairs == 5 ? 0xB5u : kPairs == 6 ? 0xEEu : 0xFFu;
   return ((kMask >> (pair & 7)) & 1u) != 0;
 }
 // exp2 of two finite scores (|x| <= 15.9, no clamp needed) on the FMA pipe: 3 FADD2 + 3 FFMA2 + 2 integer ops for the pair
@@ -295,6 +308,8 @@ __global__ void __launch_bounds__(ATT_FAST_THREADS, 1) k_attn_fast(AttnTC g) {
       const int qt = wi.qt, h = wi.h;
       const int ntok = g.group_ntok ? g.group_ntok[g.tile_group ? g.tile_group[qt] : 0] : g.ntok;
       uint64_t l2 = 0ull;                                // packed (even columns, odd columns) row sums: one FADD2 per pair
+      const float cshift = g.head_shift ? g.head_shift[h] : 0.f;       // 0 unless the head's measured score bound exceeds 15.9
+      const uint64_t cshift2 = pack_f2(cshift, cshift);
       if constexpr (kTimers) tk0 = clock64();
       // Every barrier round trip of these warps queues behind the MUFU instructions already in the SM's MIO pipe (the
       // kernel's bottleneck): a wait costs ~450 clk even when the barrier completed long ago (instrumented: wait S 497,
@@ -315,6 +330,14 @@ __global__ void __launch_bounds__(ATT_FAST_THREADS, 1) k_attn_fast(AttnTC g) {
         HY3D_TICK(1)
         const int valid = ntok - j * 128 - hh * 64;    // columns >= valid are padding tokens (last tile of a ragged count)
         bool pv_ok = j == 0, s_ok = false;
+        if (cshift != 0.f) {                           // (warp-uniform) s - c_h: one FADD2 per pair, only for heads that need it
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float x0, x1;
+            unpack_f2(sub_f2(pack_f2(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])), cshift2), x0, x1);
+            sv[2 * i] = __float_as_uint(x0); sv[2 * i + 1] = __float_as_uint(x1);
+          }
+        }
         if (valid >= 64) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {               // in place: sv[i] <- packed (p[2i], p[2i+1])
@@ -353,7 +376,15 @@ __global__ void __launch_bounds__(ATT_FAST_THREADS, 1) k_attn_fast(AttnTC g) {
       float* ls = lsum + a * 256;
       { float l0, l1; unpack_f2(l2, l0, l1); ls[hh * 128 + r] = l0 + l1; }
       asm volatile("bar.sync %0, 256;" ::"r"(1 + a) : "memory");
-      const float inv = 1.f / (ls[r] + ls[128 + r]);
+      const float lrow = ls[r] + ls[128 + r];
+      const float inv = 1.f / lrow;
+      if (g.redo_count && cshift != 0.f && lrow < (float)ntok * 0x1p-14f && hh == 0) {
+        // fp16 probabilities below 2^-14 are subnormal (absolute error up to 2^-25 each): with ntok of them the row sum is
+        // only guaranteed to 2^-11 relative (the precision of a normal fp16 term) while it stays above ntok * 2^-14.  Rows
+        // below that — every score far under the head's bound — are recomputed exactly: flag the (tile, head pair)
+        const int e = qt * (g.H >> 1) + (h >> 1);
+        if (atomicExch(&g.redo_flag[e], 1) == 0) g.redo_list[atomicAdd(g.redo_count, 1)] = e;
+      }
       mbar_wait(B.pvdone(a), pv_ph); pv_ph ^= 1;
       fence_after_sync();
       uint8_t* tile = g.O + ((size_t)qt * (g.split_out ? 3 : 1) * g.H + h) * TILE_BYTES;

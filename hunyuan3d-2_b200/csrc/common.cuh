@@ -49,8 +49,10 @@ struct DecoderWeights {
   const float *cs_kv, *bb_kv;
   const __half* t_cpx; const float* b_cpx;               // [c_proj | query_proj] K-concatenated image and b_o + b_qp (fused residual)
   const __half* t_cq3;
-  float attn_bound = 0.f;              // upper bound of |q.k| scale log2e from the q/k norm weights (inf without qk_norm)
-  bool attn_fast = false;              // bound <= 14: the attention kernel without a running maximum is exact (attention_tc.cuh)                                    // c_q split [W_hi | W_hi | W_lo], K = 3W (fp32-grade q for KV selection)
+  float attn_bound = 0.f;              // upper bound of |q.k| scale log2e from the q/k norm WEIGHTS alone (inf without qk_norm)
+  float attn_qbound = 0.f;             // upper bound of ||q|| (after q_norm) from the q-norm weights: sqrt(d) max|w| + ||b||
+  bool attn_fast = false;              // q/k norms present: the bounded-score attention kernel applies (attention_tc.cuh), with a
+                                       // per-head shift from the measured max ||k|| (KVState::head_shift) when the weight-only bound is above 15.9
 };
 
 struct KVState {
@@ -59,6 +61,9 @@ struct KVState {
   int Mpad = 0;                       // tokens padded to 128
   DevBuf k32, v32;                    // fp32 [H, M, D] (after k_norm) — SIMT path + selection
   DevBuf ktile, vtile;                // fp16 UMMA tiles — tcgen05 path
+  DevBuf head_shift;                  // float [H] per-head score shift c_h of the bounded-score attention kernel + float [H] measured score bounds
+  bool shifted = false;               // some c_h may be > 0: the exact redo pass follows every bounded-score launch
+  DevBuf redo;                        // int [1 + items] count + list of (query tile, head pair) items to recompute, then int flags per item
 };
 
 // FlashVDM per-group K/V selection (attention_processors.py:35-96): gathered token subsets as UMMA tiles
@@ -130,7 +135,7 @@ struct hy3d_ctx {
   int gemm_max_clusters[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // co-resident CTA pairs per GEMM epilogue variant
   std::vector<float> axis_host;       // last per-axis coordinate tables uploaded to ws[11] (skips the upload when unchanged)
   // diagnostics: per-stage activations of the last decoded chunk (hy3d_debug_retain / hy3d_debug_fetch)
-  int attn_poly = 2;                  // bounded-score attention kernel: PAIRS of every 8 pairs of exponentials evaluated as packed polynomials on the FMA pipe (HY3D_ATTN_POLY: 0 none, 1 = 2/16, 2 = 4/16 default, 3 = 6/16, 4 = 8/16; any other value = default)
+  int attn_poly = 4;                  // bounded-score attention kernel: PAIRS of every 8 pairs of exponentials evaluated as packed polynomials on the FMA pipe (HY3D_ATTN_POLY: 0 none, 1 .. 6 = that many pairs, 8 = all; default 4 = half of the exponentials; any other value = default)
   int debug_retain = 0;
   long long chunk_points = 262144;    // decoder chunk (HY3D_CHUNK; 131072 measured 1 % slower, 32768 7 % slower): activations of one chunk are what the stages hand over through L2 / HBM
   int xbits = 0;                      // HY3D_DBG: experiment bits for tools/gpu_chain_bench.py (results are garbage when set)
@@ -206,6 +211,7 @@ int hy3d_decode_tc_groups(hy3d_ctx* ctx, const QuerySource& src, long long n, fl
 // q after q_norm (unscaled), ~fp32 accuracy via 3-term split fp16 tensor GEMMs: d_q row-major [ceil128(n), W]
 int hy3d_tc_sample_q(hy3d_ctx* ctx, const QuerySource& src, long long n, float* d_q);
 int hy3d_tc_prepare_kv(hy3d_ctx* ctx);
+int hy3d_tc_head_shift(hy3d_ctx* ctx);
 int hy3d_tc_project_kv(hy3d_ctx* ctx, const float* d_latents, int M);   // tensor-path K/V projection (replaces simt prepare + tc prepare)
 int hy3d_simt_prepare_kv(hy3d_ctx* ctx, const float* d_latents, int M);
 

@@ -179,8 +179,13 @@ __global__ void k_head_out(const float* __restrict__ x, long long rows, int W, c
   for (int o = 16; o; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
   if (lane == 0) {
     long long oi = row;
-    if (out_mode == 1) { oi = src.index[row]; if (oi < 0) return; }
-    out[oi] = dot + bout[0];
+    float v = dot + bout[0];
+    if (out_mode == 1) {
+      oi = src.index[row];
+      if (oi < 0) return;
+      if (v == HY3D_SENTINEL) v = __int_as_float(0x7fc00000);      // see k_head_final (decoder_tc.cu)
+    }
+    out[oi] = v;
   }
 }
 

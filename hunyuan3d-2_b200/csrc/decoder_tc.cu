@@ -606,8 +606,16 @@ __global__ void __launch_bounds__(128) k_head_final(const float* __restrict__ st
   merge_row_stats<3>(st + (size_t)qi * S * 3, S, n_p, 1e-5f, mean, rstd, &dot);
   const float v = ln_post ? rstd * (dot - mean * __ldg(c12)) + __ldg(c12 + 1) : dot + __ldg(c12 + 1);
   long long oi = qi;
-  if (out_mode == 1) { oi = src.index[qi]; if (oi < 0) return; }
-  out[oi] = v;
+  float w = v;
+  if (out_mode == 1) {
+    oi = src.index[qi];
+    if (oi < 0) return;
+    // scattered into a sparse level: a logit that equals the "unvisited" sentinel IS unvisited to everything downstream
+    // (volume_decoders.py:275 turns it into NaN; the next refinement treats both alike) — written as NaN right here, so the
+    // last level can be pre-filled with NaN and needs no full-grid sentinel pass afterwards
+    if (v == HY3D_SENTINEL) w = __int_as_float(0x7fc00000);
+  }
+  out[oi] = w;
 }
 
 // head constants: dotw = gamma_post * wout (or wout), c12 = {sum dotw, beta_post . wout + bout}
@@ -800,9 +808,17 @@ int launch_attn_kernel(hy3d_ctx* ctx, K kern, const AttnTC& a, int threads) {
   kern<<<grid, threads, ATT_SMEM, ctx->stream>>>(a);
   return 0;
 }
-int launch_attn(hy3d_ctx* ctx, AttnTC a, bool fast, int fam) {
-  HY3D_PROF(ctx, fam);
+int launch_attn(hy3d_ctx* ctx, AttnTC a, bool fast, int fam, bool shifted = false) {
   if (ctx->xbits & 0x20) fast = false;
+  KVState& kv = ctx->kv;
+  if (fast && shifted) {                                   // decoder attention with measured per-head bounds (k_head_shift)
+    const size_t items = (size_t)a.Pb * (a.H / 2);
+    HY3D_CUDA(ctx, kv.redo.reserve((1 + 2 * items) * sizeof(int)));
+    HY3D_CUDA(ctx, cudaMemsetAsync(kv.redo.p, 0, (1 + 2 * items) * sizeof(int), ctx->stream));
+    a.head_shift = kv.head_shift.as<float>();
+    a.redo_count = kv.redo.as<int>(); a.redo_list = a.redo_count + 1; a.redo_flag = a.redo_list + items;
+  }
+  HY3D_PROF(ctx, fam);
   // one K/V set for all query tiles (no per-tile KV groups): pairs of query tiles share every K/V tile they stream
   a.share_kv = (a.tile_group == nullptr && !(ctx->xbits & 0x100)) ? 1 : 0;
   int rc = 0;
@@ -811,14 +827,17 @@ int launch_attn(hy3d_ctx* ctx, AttnTC a, bool fast, int fam) {
       void* tm = nullptr;
       HY3D_CUDA(ctx, cudaGetSymbolAddress(&tm, hy3d_tm));
       a.timers = reinterpret_cast<unsigned long long*>(tm);
-      rc = launch_attn_kernel(ctx, k_attn_fast<2, true>, a, ATT_FAST_THREADS);
+      rc = launch_attn_kernel(ctx, k_attn_fast<4, true>, a, ATT_FAST_THREADS);
     } else {
       switch (ctx->attn_poly) {            // pairs of every 8 whose exponentials run as packed polynomials on the FMA pipe
         case 0: rc = launch_attn_kernel(ctx, k_attn_fast<0, false>, a, ATT_FAST_THREADS); break;
         case 1: rc = launch_attn_kernel(ctx, k_attn_fast<1, false>, a, ATT_FAST_THREADS); break;
+        case 2: rc = launch_attn_kernel(ctx, k_attn_fast<2, false>, a, ATT_FAST_THREADS); break;
         case 3: rc = launch_attn_kernel(ctx, k_attn_fast<3, false>, a, ATT_FAST_THREADS); break;
-        case 4: rc = launch_attn_kernel(ctx, k_attn_fast<4, false>, a, ATT_FAST_THREADS); break;
-        default: rc = launch_attn_kernel(ctx, k_attn_fast<2, false>, a, ATT_FAST_THREADS); break;
+        case 5: rc = launch_attn_kernel(ctx, k_attn_fast<5, false>, a, ATT_FAST_THREADS); break;
+        case 6: rc = launch_attn_kernel(ctx, k_attn_fast<6, false>, a, ATT_FAST_THREADS); break;
+        case 8: rc = launch_attn_kernel(ctx, k_attn_fast<8, false>, a, ATT_FAST_THREADS); break;
+        default: rc = launch_attn_kernel(ctx, k_attn_fast<4, false>, a, ATT_FAST_THREADS); break;
       }
     }
   } else {
@@ -826,12 +845,25 @@ int launch_attn(hy3d_ctx* ctx, AttnTC a, bool fast, int fam) {
   }
   if (rc) return rc;
   HY3D_LAUNCH_CHECK(ctx);
+  if (fast && shifted) {
+    // exact redo of the (query tile, head pair) items the bounded-score kernel flagged (rows whose probabilities all fell
+    // below 2^-12 of their head's bound — normally none): the online-softmax kernel over the device work list.  A launch
+    // with an empty list costs a few microseconds; no host round trip decides anything.
+    AttnTC r = a;
+    r.share_kv = 0; r.head_shift = nullptr; r.redo_count = nullptr; r.redo_list = nullptr; r.redo_flag = nullptr;
+    r.work_count = a.redo_count; r.work_list = a.redo_list;
+    HY3D_PROF(ctx, fam);
+    HY3D_CUDA(ctx, cudaFuncSetAttribute(k_attn_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
+    const int items = a.Pb * (a.H / 2);
+    k_attn_tc<0><<<items < ctx->num_sms ? items : ctx->num_sms, ATT_THREADS, ATT_SMEM, ctx->stream>>>(r);
+    HY3D_LAUNCH_CHECK(ctx);
+  }
   return 0;
 }
 
 // Upper bound of |q . k| * scale * log2e for LayerNorm-ed q and k (over d = 64 head dims, affine (w, b)):
 // ||w * xhat + b|| <= sqrt(d) * max|w| + ||b||.  Reads the 4 x 64 norm parameters back once, at weight-load time.
-int attn_score_bound(hy3d_ctx* ctx, const float* qw, const float* qb, const float* kw, const float* kb, float* bound) {
+int attn_score_bound(hy3d_ctx* ctx, const float* qw, const float* qb, const float* kw, const float* kb, float* bound, float* qbound = nullptr) {
   float h[4][64];
   const float* src[4] = {qw, qb, kw, kb};
   HY3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -843,7 +875,35 @@ int attn_score_bound(hy3d_ctx* ctx, const float* qw, const float* qb, const floa
     n[i] = 8.f * mw + sqrtf(nb);
   }
   *bound = n[0] * n[1] * 0.125f * LOG2E;
+  if (qbound) *qbound = n[0];
   return 0;
+}
+
+// Per head: max over tokens of ||k_t|| (the K the attention kernel will see, after k_norm) -> the head's true score bound
+// B_h = qbound * max||k|| * scale * log2e and its shift c_h = max(0, B_h - 15.9): exp2(s - c_h) can then never overflow fp16
+// whatever the norm gains of the checkpoint are.  k32: fp32 [H, M, 64].  out: shift[H] then bound[H].
+constexpr float ATT_SHIFT_MAX_BOUND = 40.f;     // beyond this the weight-only bound sends the decoder to the online-softmax kernel
+__global__ void __launch_bounds__(256) k_head_shift(const float* __restrict__ k32, int M, float qbound, float* __restrict__ out, int H) {
+  const int h = blockIdx.x;
+  float mx = 0.f;
+  for (int t = threadIdx.x; t < M; t += 256) {
+    const float4* kr = reinterpret_cast<const float4*>(k32 + ((size_t)h * M + t) * 64);
+    float s = 0.f;
+#pragma unroll
+    for (int d4 = 0; d4 < 16; ++d4) { const float4 v = __ldg(kr + d4); s = fmaf(v.x, v.x, s); s = fmaf(v.y, v.y, s); s = fmaf(v.z, v.z, s); s = fmaf(v.w, v.w, s); }
+    mx = fmaxf(mx, s);
+  }
+  __shared__ float red[8];
+  for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
+    // fp16 rounding of q and k (2^-11 relative each) and of the product sum: 0.2 % head-room on the bound
+    const float b = qbound * sqrtf(mx) * 0.125f * LOG2E * 1.002f;
+    out[h] = fmaxf(b - ATT_FAST_BOUND, 0.f);
+    out[H + h] = b;
+  }
 }
 
 }  // namespace
@@ -893,12 +953,15 @@ int hy3d_tc_prepare_weights(hy3d_ctx* ctx) {
   __half* p_cq3 = p_mp + n_mp;
   if (int rc = build(w.cq_w, (int)W, (int)(3 * W), (int)W, 2, p_cq3)) return rc;
   w.t_qp = p_qp; w.t_cq = p_cq; w.t_cproj = p_cp; w.t_fc = p_fc; w.t_mp = p_mp; w.t_cq3 = p_cq3;
-  w.attn_bound = INFINITY; w.attn_fast = false;
+  w.attn_bound = INFINITY; w.attn_qbound = INFINITY; w.attn_fast = false;
   if (w.qk_norm) {
-    if (int rc = attn_score_bound(ctx, w.qn_w, w.qn_b, w.kn_w, w.kn_b, &w.attn_bound)) return rc;
-    w.attn_fast = w.attn_bound <= ATT_FAST_BOUND;
+    if (int rc = attn_score_bound(ctx, w.qn_w, w.qn_b, w.kn_w, w.kn_b, &w.attn_bound, &w.attn_qbound)) return rc;
+    // bounded-score kernel whenever q/k norms bound the scores at all; above 15.9 (weight-only bound) the per-head shift from
+    // the MEASURED max ||k|| of each latent set (k_head_shift) keeps exp2 inside fp16 and an exact redo pass covers the rows
+    // whose scores sit far below their head's bound (hy3d_tc_head_shift, launch_attn)
+    w.attn_fast = w.attn_bound <= ATT_SHIFT_MAX_BOUND;
   }
-  if (getenv("HY3D_VERBOSE")) fprintf(stderr, "[hy3dgeo] decoder attention score bound %.3f -> %s kernel\n", w.attn_bound, w.attn_fast ? "bounded-score" : "online-softmax");
+  if (getenv("HY3D_VERBOSE")) fprintf(stderr, "[hy3dgeo] decoder attention score bound (weights) %.3f -> %s kernel\n", w.attn_bound, w.attn_fast ? "bounded-score" : "online-softmax");
   // per-latent K/V projection on the tensor path (hy3d_tc_project_kv): ln_2 folded into c_kv, rows permuted
   // [head][k|v][64] -> [k | v], 3-term split (fp32-grade: K/V feed every query and the FlashVDM token selection)
   w.t_ckv3 = nullptr; w.t_lp3 = nullptr;
@@ -933,6 +996,20 @@ int hy3d_tc_prepare_weights(hy3d_ctx* ctx) {
   return 0;
 }
 
+// Measured per-head score bounds of the K just prepared (kv.k32) -> kv.head_shift; see k_head_shift.
+int hy3d_tc_head_shift(hy3d_ctx* ctx) {
+  DecoderWeights& w = ctx->w;
+  KVState& kv = ctx->kv;
+  kv.shifted = false;
+  if (!w.attn_fast) return 0;
+  HY3D_CUDA(ctx, kv.head_shift.reserve((size_t)2 * w.H * sizeof(float)));
+  HY3D_PROF(ctx, FAM_KV);
+  k_head_shift<<<w.H, 256, 0, ctx->stream>>>(kv.k32.as<float>(), kv.M, w.attn_qbound, kv.head_shift.as<float>(), w.H);
+  HY3D_LAUNCH_CHECK(ctx);
+  kv.shifted = w.attn_bound > ATT_FAST_BOUND;          // weight-only bound already safe: every c_h is 0, no redo pass needed
+  return 0;
+}
+
 int hy3d_tc_prepare_kv(hy3d_ctx* ctx) {
   DecoderWeights& w = ctx->w;
   if (!w.t_qp) return 0;
@@ -946,7 +1023,7 @@ int hy3d_tc_prepare_kv(hy3d_ctx* ctx) {
   k_build_kv<<<(unsigned)ceil_div64(total, 256), 256, 0, ctx->stream>>>(kv.k32.as<float>(), kv.v32.as<float>(), w.H, kv.M, nkv,
                                                                         kv.ktile.as<uint8_t>(), kv.vtile.as<uint8_t>());
   HY3D_LAUNCH_CHECK(ctx);
-  return 0;
+  return hy3d_tc_head_shift(ctx);
 }
 
 namespace {
@@ -1033,7 +1110,7 @@ int hy3d_tc_project_kv(hy3d_ctx* ctx, const float* d_latents, int M) {
   g.K32 = kv.k32.as<float>(); g.V32T = kv.v32.as<float>(); g.Mtok = M;
   if (int rc = launch_gemm<EPI_QKV>(ctx, g, FAM_KV)) return rc;
   kv.M = M; kv.Mpad = (int)Mp; kv.ready = true;
-  return 0;
+  return hy3d_tc_head_shift(ctx);
 }
 
 static int decode_tc_impl(hy3d_ctx* ctx, const QuerySource& src_in, long long n, float* d_out, int out_mode, const int* d_tile_group) {
@@ -1095,7 +1172,7 @@ static int decode_tc_impl(hy3d_ctx* ctx, const QuerySource& src_in, long long n,
       } else {
         a.K = ctx->kv.ktile.as<uint8_t>(); a.V = ctx->kv.vtile.as<uint8_t>(); a.nkv = ctx->kv.Mpad / 128; a.ntok = ctx->kv.M;
       }
-      if (int rc = launch_attn(ctx, a, w.attn_fast, FAM_ATTN)) return rc;
+      if (int rc = launch_attn(ctx, a, w.attn_fast, FAM_ATTN, ctx->kv.shifted)) return rc;
     }
     if (int rc = hy3d_debug_keep(ctx, 3, tq, (size_t)Pp * W * 2, 2, Pp, W)) return rc;
     // x1 = x0 + c_proj(attn): fp32 residual in place + raw fp16 copy + statistics for the folded ln_3
@@ -1267,7 +1344,7 @@ extern "C" int hy3d_set_transformer_weights(hy3d_ctx* ctx, const hy3d_transforme
     if (d->qk_norm) {
       float bound = INFINITY;
       if (int rc = attn_score_bound(ctx, y.q_norm_w, y.q_norm_b, y.k_norm_w, y.k_norm_b, &bound)) return rc;
-      t.attn_fast[l] = bound <= ATT_FAST_BOUND ? 1 : 0;
+      t.attn_fast[l] = bound <= ATT_FAST_BOUND ? 1 : 0;       // (weight-only bound: the self-attention launches are 16 x 90 us)
     }
   }
   HY3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // the fold scratch (ws[10]) is reused by other calls

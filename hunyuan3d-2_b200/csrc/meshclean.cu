@@ -135,15 +135,15 @@ extern "C" int hy3d_mesh_clean(hy3d_ctx* ctx, const float* d_verts, int64_t nV, 
   HY3D_CUDA(ctx, cudaSetDevice(ctx->device));
   const int nbV = (int)ceil_div64(nV, CL_BLOCK), nbF = (int)ceil_div64(nF, CL_BLOCK);
   const size_t aV = ((size_t)nV + 255) / 256 * 256, aF = ((size_t)nF + 255) / 256 * 256;
-  const size_t bytes = aV + aF + aV * 4 + ((size_t)nbV + nbF + 64) * 4 + ((size_t)nbV + nbF + 66) * 8;
+  const size_t bytes = aV + aF + aV * 4 + ((size_t)nbV + nbF + 128) * 4 + ((size_t)nbV + nbF + 66) * 8;
   HY3D_CUDA(ctx, ctx->scratch.reserve(bytes));
   uint8_t* vref = ctx->scratch.as<uint8_t>();
   uint8_t* fkeep = vref + aV;
   int32_t* remap = reinterpret_cast<int32_t*>(fkeep + aF);
   int* cntV = remap + aV;
-  int* cntF = cntV + nbV + 32;
-  long long* offV = reinterpret_cast<long long*>(cntF + nbF + 32);
-  long long* offF = offV + nbV + 33;
+  int* cntF = cntV + (nbV + 63) / 64 * 64;
+  long long* offV = reinterpret_cast<long long*>(cntF + (nbF + 63) / 64 * 64);      // 256-byte multiples keep the 8-byte alignment
+  long long* offF = offV + (nbV + 1 + 31) / 32 * 32;
   HY3D_CUDA(ctx, cudaMemsetAsync(vref, 0, aV, ctx->stream));
   HY3D_PROF(ctx, FAM_MC_EMIT);
   k_face_flags<<<(unsigned)ceil_div64(nF, 256), 256, 0, ctx->stream>>>(d_verts, nV, d_faces, nF, fkeep, vref);

@@ -163,7 +163,10 @@ __global__ void k_scatter_f32(const int32_t* __restrict__ index, const float* __
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
   int i = index[t];
-  if (i >= 0) grid[i - base] = vals[t];
+  if (i < 0) return;
+  float v = vals[t];
+  if (v == HY3D_SENTINEL) v = __int_as_float(0x7fc00000);    // a logit equal to the sentinel is "unvisited" downstream (volume_decoders.py:275)
+  grid[i - base] = v;
 }
 
 __global__ void k_sentinel_nan(float* __restrict__ p, long long n, float sentinel) {

@@ -395,11 +395,10 @@ class ShardedHierarchicalVolumeDecoding:
                     p_hi = min(planes[rank + 1] + MC_HALO, n)
                     part = index[starts[rank]: ends[rank]]
                     slab = torch.empty((p_hi - plane0, n, n), dtype=torch.float32, device=latents.device)
-                    ctx.fill(slab, SENTINEL)
+                    ctx.fill(slab, float("nan"))           # unvisited = NaN from the start: no sentinel sweep afterwards
                     if part.numel():
                         vals = ctx.decode_list_values(part, (n, n, n), cell, bmin32)
                         ctx.scatter(part, vals, slab, base=plane0 * n * n)
-                    ctx.sentinel_to_nan(slab, SENTINEL)
                     grid = slab
                     plane0s.append(plane0); owns.append(own)
                     mine.append(int(part.numel()))

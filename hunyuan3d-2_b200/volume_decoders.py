@@ -25,6 +25,7 @@ from . import weights as W
 from ._lib import GeoContext, get_context
 
 SENTINEL = -10000.0
+NAN = float("nan")
 
 
 def normalize_bounds(bounds) -> np.ndarray:
@@ -161,9 +162,12 @@ class HierarchicalVolumeDecoding:
             kept = [grid]
             for r in levels[1:]:
                 n = r + 1
-                index = refine_level(ctx, grid, mc_level, last=(r == levels[-1]), nf=n)
+                last = r == levels[-1]
+                index = refine_level(ctx, grid, mc_level, last=last, nf=n)
                 nxt = torch.empty((n, n, n), dtype=torch.float32, device=latents.device)
-                ctx.fill(nxt, SENTINEL)
+                # the last level is born with NaN at the unvisited voxels (reference :245-246 + :275 in one pass: the
+                # 228 MB sentinel -> NaN sweep over a 385^3 grid is gone); intermediate levels keep the -10000 sentinel
+                ctx.fill(nxt, NAN if last and not self.keep_levels else SENTINEL)
                 cell = (bbox_size / r).astype(np.float32)           # reference :243,:394 float32(resolution)
                 ctx.decode_list(index, index.numel(), (n, n, n), cell, bbox_min.astype(np.float32), nxt)
                 grid = nxt
@@ -171,7 +175,8 @@ class HierarchicalVolumeDecoding:
                 kept.append(grid)
             if self.keep_levels:
                 self.last_levels = kept[:-1] + [kept[-1].clone()]
-            ctx.sentinel_to_nan(grid, SENTINEL)
+            if self.keep_levels or len(levels) == 1:
+                ctx.sentinel_to_nan(grid, SENTINEL)
             outs.append(grid)
             self.last_stats.append({"levels": levels, "queries": queries})
         return torch.stack(outs, 0).to(latents.dtype)
@@ -268,7 +273,7 @@ class FlashVDMVolumeDecoding:
                 cell = (bbox_size / r).astype(np.float32)
                 bmin32 = bbox_min.astype(np.float32)
                 nxt = torch.empty((n, n, n), dtype=torch.float32, device=dev)
-                ctx.fill(nxt, SENTINEL)
+                ctx.fill(nxt, NAN if r == levels[-1] and not self.keep_levels else SENTINEL)     # see HierarchicalVolumeDecoding
                 nq = int(index.numel())
                 queries.append(nq)
                 if nq:
@@ -292,7 +297,8 @@ class FlashVDMVolumeDecoding:
                 kept.append(grid)
             if self.keep_levels:
                 self.last_levels = kept[:-1] + [kept[-1].clone()]
-            ctx.sentinel_to_nan(grid, SENTINEL)
+            if self.keep_levels or len(levels) == 1:
+                ctx.sentinel_to_nan(grid, SENTINEL)
             outs.append(grid)
             self.last_stats.append({"levels": levels, "queries": queries})
         return torch.stack(outs, 0).to(latents.dtype)

@@ -77,10 +77,12 @@ int hy3d_set_precision(hy3d_ctx* ctx, int precision);
 /* Count of kernels this library has launched on ctx since creation (bench `gpu_launches`). */
 int64_t hy3d_launch_count(const hy3d_ctx* ctx);
 
-/* Which attention kernel the loaded decoder weights select (bench / diagnostics): *h_score_bound = the upper bound of
- * |q.k| * scale * log2(e) derived from the q/k-norm weights (+inf without q/k norm), *h_bounded_kernel = 1 when the
- * bounded-score softmax kernel runs, 0 for the online-softmax kernel (csrc/attention_tc.cuh). */
-int hy3d_attention_info(const hy3d_ctx* ctx, float* h_score_bound, int32_t* h_bounded_kernel);
+/* Which attention kernel runs for the loaded decoder weights and the K/V prepared last (bench / diagnostics; synchronises the
+ * stream when h_measured_bound is given).  *h_score_bound = upper bound of |q.k| * scale * log2(e) from the q/k-norm WEIGHTS
+ * alone (+inf without q/k norm); *h_measured_bound = the same with the measured max ||k|| of the current latent set per head
+ * (largest over heads); *h_bounded_kernel = 0 online-softmax kernel, 1 bounded-score kernel, 2 bounded-score kernel with
+ * per-head score shifts and the exact redo pass (weight-only bound above 15.9; csrc/attention_tc.cuh). */
+int hy3d_attention_info(hy3d_ctx* ctx, float* h_score_bound, int32_t* h_bounded_kernel, float* h_measured_bound);
 
 /* ---- latent transformer: replaces ShapeVAE.forward = post_kl + Transformer (model.py:186-189,
  * attention_blocks.py:301-432).  fp32 DEVICE pointers, nn.Linear layout, state_dict names
@@ -237,13 +239,16 @@ int hy3d_debug_retain(hy3d_ctx* ctx, int enable);
  * bounded-score attention kernel (hy3d_debug_timers), 0x10000 the CUDA-core K/V projection (results stay valid);
  * 0x100 gives every attention stream its own K/V ring even when all query tiles share one K/V set;
  * `attn_poly` = pairs of every 8 pairs of attention exponentials evaluated as packed polynomials on the FMA pipe
- * (0 none, 1 = 2/16, 2 = 4/16, 3 = 6/16, 4 = 8/16; other values select the default, 2).
- * Defaults (0, 2) are the product configuration. */
+ * (0 none, 1 .. 6 = that many pairs, 8 = all; other values select the default, 4 = half of the exponentials).
+ * Defaults (0, 4) are the product configuration. */
 int hy3d_debug_experiment(hy3d_ctx* ctx, int bits, int attn_poly);
 /* Phase clocks accumulated by the instrumented attention kernel (experiment bit 0x40), returned and cleared:
  * per head stream a (0, 1) h_out[8a + i] = SM cycles one softmax thread of CTA 0 spent in phase i
  * (0 wait S, 1 load S, 2 exponentials, 3 wait PV, 4 store P, 5 finalize), h_out[8a + 7] = KV tiles. */
 int hy3d_debug_timers(hy3d_ctx* ctx, uint64_t h_out[32]);
+/* (query tile, head pair) items the exact redo pass recomputed after the LAST bounded-score attention launch with per-head
+ * shifts (normally 0; see hy3d_attention_info).  Synchronises the stream. */
+int hy3d_debug_attn_redo(hy3d_ctx* ctx, int32_t* h_items);
 /* Row-major fp32 [rows, *h_width] copy of a retained stage, whatever its internal layout. */
 int hy3d_debug_fetch(hy3d_ctx* ctx, int stage, float* d_out, int64_t rows, int32_t* h_width);
 

@@ -634,3 +634,69 @@ def test_mesh_clean_matches_export_to_trimesh_restatement(dev, ctx):
     assert torch.equal(vo, v) and torch.equal(fo, f.flip(1))
     vo, fo = ctx.mesh_clean(torch.full_like(v, float("nan")), f, flip_winding=False)
     assert vo.shape[0] == 0 and fo.shape[0] == 0
+
+
+# ------------------------------------------------- attention: measured score bounds, per-head shift, exact redo pass
+def _scaled_norms(cfg, gain, seed=0):
+    sd = W.synthetic_state_dict(cfg, seed=seed, with_transformer=False)
+    c = "geo_decoder.cross_attn_decoder.attn.attention."
+    for n in ("q_norm", "k_norm"):
+        sd[c + n + ".weight"] = sd[c + n + ".weight"] * gain
+    return sd
+
+
+def test_attention_large_norm_gains_use_measured_bounds(dev, ctx):
+    """A checkpoint whose q/k-norm gains put the weight-only score bound above 15.9 (here x1.4 each: ~30) still runs the
+    bounded-score kernel: each head's scores are shifted by its MEASURED bound (max ||k|| of the latent set) minus 15.9, so
+    exp2 cannot overflow fp16, and rows too far below the bound are recomputed exactly.  Logits vs the fp32 device path."""
+    cfg = W.MINI
+    sd = _scaled_norms(cfg, 1.4)
+    gd = hy3dgeo.GeoDecoder(W.geo_decoder_state(sd), cfg)
+    lat = torch.randn(1, 512, 1024, generator=torch.Generator().manual_seed(3)).to(dev)
+    c = bind(lat, gd)
+    c.prepare_kv(lat[0])
+    wb, kern, mb = c.attention_info()
+    assert 15.9 < wb < 40 and kern.startswith("bounded-score + per-head shift") and mb < wb
+    pts = ((torch.rand(3000, 3, generator=torch.Generator().manual_seed(4)) * 2 - 1) * 1.01).to(dev)
+    c.set_precision(_lib.PRECISION_FP32_SIMT)
+    ref = c.decode_points(pts).cpu()
+    c.set_precision(_lib.PRECISION_FP16_TC)
+    out = c.decode_points(pts).cpu()
+    c.check_watchdog()
+    assert float((out - ref).abs().max()) < LOGIT_TOL
+    assert c.debug_attn_redo() == 0                      # ordinary latents: nothing is far enough below the bound
+    gsd, fr = W.geo_decoder_state(sd), W.fourier_frequencies(cfg)
+    o = OD.geo_decoder_forward(gsd, pts[None, :256].cpu(), lat.cpu(), fr, cfg.dec_heads)[0, :, 0]
+    assert float((out[:256] - o).abs().max()) < LOGIT_TOL
+    # gains beyond the shift range (weight-only bound > 40): the online-softmax kernel, same answers
+    sd2 = _scaled_norms(cfg, 2.0)
+    gd2 = hy3dgeo.GeoDecoder(W.geo_decoder_state(sd2), cfg)
+    c = bind(lat, gd2)
+    c.prepare_kv(lat[0])
+    assert c.attention_info()[1] == "online-softmax"
+    c.set_precision(_lib.PRECISION_FP32_SIMT); ref = c.decode_points(pts[:512]).cpu()
+    c.set_precision(_lib.PRECISION_FP16_TC); out = c.decode_points(pts[:512]).cpu()
+    assert float((out - ref).abs().max()) < LOGIT_TOL
+
+
+def test_attention_redo_pass_recomputes_rows_far_below_the_bound(dev, ctx):
+    """Adversarial latents (all tokens nearly identical): every key of a head points the same way, so for half of the
+    queries ALL scores sit far below the head's bound; after the shift their probabilities underflow fp16.  The kernel flags
+    those (query tile, head pair) items on the device and the online-softmax kernel recomputes them: results stay exact."""
+    cfg = W.MINI
+    sd = _scaled_norms(cfg, 1.5)
+    gd = hy3dgeo.GeoDecoder(W.geo_decoder_state(sd), cfg)
+    g = torch.Generator().manual_seed(5)
+    row = torch.randn(1, 1, 1024, generator=g)
+    lat = (row + 1e-3 * torch.randn(1, 512, 1024, generator=g)).to(dev)
+    c = bind(lat, gd)
+    c.prepare_kv(lat[0])
+    assert c.attention_info()[1].startswith("bounded-score + per-head shift")
+    pts = ((torch.rand(1500, 3, generator=torch.Generator().manual_seed(6)) * 2 - 1) * 1.01).to(dev)
+    c.set_precision(_lib.PRECISION_FP32_SIMT)
+    ref = c.decode_points(pts).cpu()
+    c.set_precision(_lib.PRECISION_FP16_TC)
+    out = c.decode_points(pts).cpu()
+    c.check_watchdog()
+    assert c.debug_attn_redo() > 0, "the adversarial case was meant to exercise the redo pass"
+    assert float((out - ref).abs().max()) < LOGIT_TOL
