@@ -154,7 +154,7 @@ def main():
                     f"refinement) + marching cubes")
         weights = (f"random-init seed 0 (hy3dgeo.weights.synthetic_state_dict) + SURVEY §8d sparse-field edit: query_proj keeps Fourier "
                    f"frequencies < {SPARSE_FULL['keep_freqs']}, output_proj gain {SPARSE_FULL['gain']:.6f} bias {SPARSE_FULL['bias']:.6f}")
-        partition = (f"x{world}: level 0 axis-0 slabs, middle level equal list ranges (all-gathered), last level plane-aligned slabs kept "
+        partition = (f"x{world}: latent transformer by token ranges (K/V tiles all-gathered per layer), level 0 axis-0 slabs, middle level equal list ranges (all-gathered), last level plane-aligned slabs kept "
                      f"through sharded marching cubes" + (" [--gather: last level all-gathered, MC on rank 0]" if args.gather else "")) if world > 1 else "single GPU"
     else:
         workload = f"{name} VanillaVolumeDecoder octree_resolution={res} + marching cubes"
@@ -216,8 +216,10 @@ def main():
     mesh_bytes = [0]
     mesh_size = [0, 0]
 
+    tf_group = True if world > 1 else None        # N > 1: the latent transformer runs sequence-parallel over the ranks
+
     def step_device():
-        lat = vae(z_dev)
+        lat = vae(z_dev, group=tf_group)
         grid = vae.volume_decoder(lat, vae.geo_decoder, **kw)
         if grid is not None:
             m = vae.surface_extractor.run_device(grid[0], mc_level=0.0, bounds=1.01, octree_resolution=res)
@@ -225,7 +227,7 @@ def main():
                 mesh_size[0], mesh_size[1] = m[0].shape[0], m[1].shape[0]
 
     def step_e2e():
-        outs = vae.latents2mesh(vae(z_host.to(dev, non_blocking=True)), **kw)
+        outs = vae.latents2mesh(vae(z_host.to(dev, non_blocking=True), group=tf_group), **kw)
         if outs is not None and outs[0] is not None:
             mesh_bytes[0] = outs[0].mesh_v.nbytes + outs[0].mesh_f.nbytes
 

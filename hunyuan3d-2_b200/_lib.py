@@ -68,6 +68,10 @@ SYMBOLS = {
     "hy3d_set_decoder_weights": (C.c_int, [C.c_void_p, C.POINTER(DecoderDesc)]),
     "hy3d_set_transformer_weights": (C.c_int, [C.c_void_p, C.POINTER(TransformerDesc)]),
     "hy3d_transformer_forward": (C.c_int, [C.c_void_p, c_f32p, C.c_int32, c_f32p]),
+    "hy3d_transformer_begin": (C.c_int, [C.c_void_p, c_f32p, C.c_int32, C.c_int32, C.c_int32]),
+    "hy3d_transformer_layer_kv": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "hy3d_transformer_layer_rest": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "hy3d_transformer_end": (C.c_int, [C.c_void_p, c_f32p]),
     "hy3d_prepare_kv": (C.c_int, [C.c_void_p, c_f32p, C.c_int32]),
     "hy3d_decode_points": (C.c_int, [C.c_void_p, c_f32p, C.c_int64, c_f32p]),
     "hy3d_decode_dense": (C.c_int, [C.c_void_p, c_f32p, c_f32p, c_f32p, C.c_int32, C.c_int32, C.c_int32,
@@ -293,6 +297,40 @@ class GeoContext:
         z = z.detach().to(device=self.device, dtype=torch.float32).contiguous()
         out = torch.empty((z.shape[0], self._tf_width), dtype=torch.float32, device=self.device)
         self._check(self.lib.hy3d_transformer_forward(self.h, _ptr(z), z.shape[0], _ptr(out)), "hy3d_transformer_forward")
+        return out
+
+    def transformer_forward_parallel(self, z: torch.Tensor, heads: int, layers: int, group=None) -> torch.Tensor:
+        """Sequence-parallel ShapeVAE.forward for one item over a process group (see hy3dgeo.h): z [M, embed_dim] is known
+        on every rank, rank r runs the rows [r M / world, (r+1) M / world); per layer the K / V tile images are all-gathered
+        (NCCL), at the end the latent rows.  Returns the full latents [M, width] float32 on every rank."""
+        import torch.distributed as dist
+        self.sync_stream()
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        M = z.shape[0]
+        Ml = M // world
+        if M % world or Ml % 128:
+            raise ValueError(f"{M} tokens cannot be split into {world} parts that are multiples of 128")
+        zl = z[rank * Ml:(rank + 1) * Ml].detach().to(device=self.device, dtype=torch.float32).contiguous()
+        chunk = 2 * heads * (Ml // 128) * 16384
+        kv = torch.empty(world * chunk, dtype=torch.uint8, device=self.device)
+        staged = dist.get_backend(group) == "gloo"        # 2-process tests sharing one GPU: gloo moves host tensors only
+
+        def gather_inplace(full, part):
+            if not staged:
+                dist.all_gather_into_tensor(full, part, group=group)
+                return
+            host = torch.empty(full.shape, dtype=full.dtype)
+            dist.all_gather(list(host.view(world, -1).unbind(0)), part.reshape(-1).cpu(), group=group)
+            full.copy_(host)
+        self._check(self.lib.hy3d_transformer_begin(self.h, _ptr(zl), Ml, world, rank), "hy3d_transformer_begin")
+        for l in range(layers):
+            self._check(self.lib.hy3d_transformer_layer_kv(self.h, l, _ptr(kv)), "hy3d_transformer_layer_kv")
+            gather_inplace(kv, kv[rank * chunk:(rank + 1) * chunk])
+            self._check(self.lib.hy3d_transformer_layer_rest(self.h, l, _ptr(kv)), "hy3d_transformer_layer_rest")
+        out = torch.empty((M, self._tf_width), dtype=torch.float32, device=self.device)
+        mine = out[rank * Ml:(rank + 1) * Ml]
+        self._check(self.lib.hy3d_transformer_end(self.h, _ptr(mine)), "hy3d_transformer_end")
+        gather_inplace(out, mine)
         return out
 
     def prepare_kv(self, latents: torch.Tensor):

@@ -52,6 +52,9 @@ struct AttnTC {
   int Pb, H, nkv, ntok;  // nkv = tiles per (group, head); ntok = valid tokens when group_ntok == null
   int split_out;         // O written as [hi | lo | hi] over 3H k-blocks (operand of a 3-term split GEMM)
   int share_kv;          // 1: streams = two query tiles of one head sharing every K/V tile; 0: two heads of one query tile
+  // K / V gathered from several GPUs (sequence-parallel latent transformer): tile j of head h lives in chunk j / kv_tpr at
+  // K + (j / kv_tpr) * kv_chunk_stride + (h * kv_tpr + j % kv_tpr) * 16 KB (same for V).  kv_tpr = 0: one chunk of nkv tiles.
+  int kv_tpr; long long kv_chunk_stride;
   // bounded-score kernel with measured bounds: p = exp2(s - head_shift[h]); rows whose sum falls below ntok * 2^-14 (all their
   // scores far below the head's bound: the fp16 probabilities would be subnormal) flag their (tile, head pair) for an exact redo
   const float* head_shift;      // [H] or null (no shift)
@@ -153,12 +156,16 @@ __device__ __forceinline__ void attn_producer(const AttnTC& g, const AttnBars& B
     }
     qph ^= 1;
     const int grp = g.tile_group ? g.tile_group[it.qt] : 0;
-    const uint8_t* kb = g.K + ((size_t)grp * g.H + it.h) * nkv * TILE_BYTES;
-    const uint8_t* vb = g.V + ((size_t)grp * g.H + it.h) * nkv * TILE_BYTES;
-    push(kb);
+    const int tpr = g.kv_tpr ? g.kv_tpr : nkv;
+    const size_t head_off = ((size_t)grp * g.H + it.h) * tpr * TILE_BYTES;
+    auto tile = [&](const uint8_t* base, int j) {
+      return g.kv_tpr ? base + (size_t)(j / tpr) * g.kv_chunk_stride + head_off + (size_t)(j % tpr) * TILE_BYTES
+                      : base + head_off + (size_t)j * TILE_BYTES;
+    };
+    push(tile(g.K, 0));
     for (int j = 0; j < nkv; ++j) {
-      if (j + 1 < nkv) push(kb + (size_t)(j + 1) * TILE_BYTES);
-      push(vb + (size_t)j * TILE_BYTES);
+      if (j + 1 < nkv) push(tile(g.K, j + 1));
+      push(tile(g.V, j));
     }
   }
 }

@@ -80,6 +80,7 @@ struct KVSelState {
 struct TransformerState {
   bool set = false;
   int L = 0, W = 0, H = 0, E = 0, R = 4, qk_norm = 0;
+  int Ml = 0, parts = 1, part = 0;     // forward pass in progress: local tokens, token-range parts (GPUs), this part
   DevBuf tc;                          // fp16 B16 images, 3-term split: post_kl, per layer c_qkv (LN-folded, rows permuted), c_proj, c_fc (LN-folded), mlp.c_proj
   DevBuf f32;                         // per layer: cs_qkv, bb_qkv, b_proj, cs_fc, bb_fc, b_proj2, q/k norm; post_kl bias
   std::vector<const uint8_t*> t_qkv, t_proj, t_fc, t_proj2;

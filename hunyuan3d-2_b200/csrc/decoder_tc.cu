@@ -135,6 +135,21 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return fmaxf(x, 0.f) - ax * e;
 }
 
+// gelu_erf<3> of two values with the polynomial on packed f32x2 instructions (FMUL2 / FFMA2: one issue slot for the pair):
+// 8 instead of 12.5 issue slots per element in the c_fc epilogue, which is what paces that GEMM (epilogue ~ MMA time).
+__device__ __forceinline__ void gelu_erf3_pair(float x0, float x1, float& y0, float& y1) {
+  float u0, u1;
+  unpack_f2(mul_f2(pack_f2(x0, x1), pack_f2(0.70710678118654752440f, 0.70710678118654752440f)), u0, u1);
+  const uint64_t t = pack_f2(fminf(fabsf(u0), 4.0f), fminf(fabsf(u1), 4.0f));
+  uint64_t g = fma_f2(pack_f2(1.664811e-02f, 1.664811e-02f), t, pack_f2(-1.2936552e-01f, -1.2936552e-01f));     // -g(t)
+  g = fma_f2(g, t, pack_f2(-9.2985345e-01f, -9.2985345e-01f));
+  g = fma_f2(g, t, pack_f2(-1.62573555e+00f, -1.62573555e+00f));
+  float a0, a1;
+  unpack_f2(fma_f2(t, g, pack_f2(-1.0f, -1.0f)), a0, a1);             // -t g(t) - 1
+  y0 = fmaf(-fabsf(x0), ex2(a0), fmaxf(x0, 0.f));
+  y1 = fmaf(-fabsf(x1), ex2(a1), fmaxf(x1, 0.f));
+}
+
 __device__ __forceinline__ void store_t16_chunk(uint8_t* tile, int r, int c16, const float* v) {
   uint4 u;
   u.x = pack_h2(v[0], v[1]); u.y = pack_h2(v[2], v[3]); u.z = pack_h2(v[4], v[5]); u.w = pack_h2(v[6], v[7]);
@@ -303,10 +318,11 @@ k_gemm_tc(GemmTC g, const __grid_constant__ CUtensorMap tmA, const __grid_consta
           float4 bv = g.bias ? __ldg(b4 + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
           const float a0 = __uint_as_float(v[4 * i4]), a1 = __uint_as_float(v[4 * i4 + 1]);
           const float a2 = __uint_as_float(v[4 * i4 + 2]), a3 = __uint_as_float(v[4 * i4 + 3]);
-          if (fold) {
+          if (fold) {           // rstd * a + (nm * cs + b) on packed pairs: 2 FFMA2 per pair instead of 4 FFMA
             const float4 cv = __ldg(c4 + i4);
-            x[4 * i4] = fmaf(ln_rstd, a0, fmaf(nm, cv.x, bv.x)); x[4 * i4 + 1] = fmaf(ln_rstd, a1, fmaf(nm, cv.y, bv.y));
-            x[4 * i4 + 2] = fmaf(ln_rstd, a2, fmaf(nm, cv.z, bv.z)); x[4 * i4 + 3] = fmaf(ln_rstd, a3, fmaf(nm, cv.w, bv.w));
+            const uint64_t r2 = pack_f2(ln_rstd, ln_rstd), n2 = pack_f2(nm, nm);
+            unpack_f2(fma_f2(r2, pack_f2(a0, a1), fma_f2(n2, pack_f2(cv.x, cv.y), pack_f2(bv.x, bv.y))), x[4 * i4], x[4 * i4 + 1]);
+            unpack_f2(fma_f2(r2, pack_f2(a2, a3), fma_f2(n2, pack_f2(cv.z, cv.w), pack_f2(bv.z, bv.w))), x[4 * i4 + 2], x[4 * i4 + 3]);
           } else {
             x[4 * i4] = a0 + bv.x; x[4 * i4 + 1] = a1 + bv.y; x[4 * i4 + 2] = a2 + bv.z; x[4 * i4 + 3] = a3 + bv.w;
           }
@@ -420,7 +436,7 @@ k_gemm_tc(GemmTC g, const __grid_constant__ CUtensorMap tmA, const __grid_consta
               for (int i = 0; i < 32; ++i) x[i] = gelu_erf<5>(x[i]);
             } else {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) x[i] = gelu_erf<3>(x[i]);
+              for (int i = 0; i < 32; i += 2) gelu_erf3_pair(x[i], x[i + 1], x[i], x[i + 1]);
             }
             const int KBn = g.N / 64;
             uint8_t* tile = g.Tout + ((size_t)mb * (g.split_out ? 3 : 1) * KBn + (c >> 6)) * TILE_BYTES;
@@ -1352,69 +1368,107 @@ extern "C" int hy3d_set_transformer_weights(hy3d_ctx* ctx, const hy3d_transforme
   return HY3D_OK;
 }
 
-extern "C" int hy3d_transformer_forward(hy3d_ctx* ctx, const float* d_z, int32_t M, float* d_out) {
-  if (!ctx || !d_z || !d_out || M <= 0) return HY3D_ERR_ARG;
+// ---- the forward pass in four steps, so that a latent set can be split by token ranges across GPUs (sequence parallel):
+// every GEMM, LayerNorm and residual acts on rows independently; only self-attention needs all tokens' K / V, which the
+// ranks exchange as ready-made tile images — one all-gather per layer, done by the host between layer_kv and layer_rest.
+// K / V exchange buffer: [parts][2 (K, V^T)][H][Ml / 128][16 KB]; chunk `part` is written by this rank.
+static size_t tf_chunk_bytes(const TransformerState& t) { return (size_t)2 * t.H * (t.Ml / 128) * TILE_BYTES; }
+
+extern "C" int hy3d_transformer_begin(hy3d_ctx* ctx, const float* d_z_local, int32_t Ml, int32_t parts, int32_t part) {
+  if (!ctx || !d_z_local || Ml <= 0 || parts <= 0 || part < 0 || part >= parts) return HY3D_ERR_ARG;
   TransformerState& t = ctx->tf;
   if (!t.set) return hy3d_fail(ctx, HY3D_ERR_STATE, "transformer weights not set");
-  if (M % 128) return hy3d_fail(ctx, HY3D_ERR_UNSUPPORTED, "token count must be a multiple of 128");
+  if (Ml % 128) return hy3d_fail(ctx, HY3D_ERR_UNSUPPORTED, "token count (per part) must be a multiple of 128");
   HY3D_CUDA(ctx, cudaSetDevice(ctx->device));
-  const int W = t.W, H = t.H, R = t.R, E = t.E, Mb = M / 128, S = ST_PER_TILE * (W / BN);
-  const size_t Mp = (size_t)M;
+  t.Ml = Ml; t.parts = parts; t.part = part;
+  const int W = t.W, R = t.R, E = t.E, Mb = Ml / 128, S = ST_PER_TILE * (W / BN);
+  const size_t Mp = (size_t)Ml;
   HY3D_CUDA(ctx, t.x.reserve(Mp * W * 4));
   HY3D_CUDA(ctx, t.ta.reserve(Mp * 3 * W * 2));
   HY3D_CUDA(ctx, t.tq.reserve(Mp * W * 2));
   HY3D_CUDA(ctx, t.to.reserve(Mp * 3 * W * 2));
   HY3D_CUDA(ctx, t.th.reserve(Mp * 3 * R * W * 2));
-  HY3D_CUDA(ctx, t.kt.reserve(Mp * W * 2));
-  HY3D_CUDA(ctx, t.vt.reserve(Mp * W * 2));
   HY3D_CUDA(ctx, t.st.reserve(Mp * S * 2 * 2 * 4));
   HY3D_CUDA(ctx, t.tz.reserve(Mp * 3 * E * 2));
-  float* x = t.x.as<float>();
-  uint8_t *ta = t.ta.as<uint8_t>(), *tq = t.tq.as<uint8_t>(), *to = t.to.as<uint8_t>(), *th = t.th.as<uint8_t>();
-  float* stA = t.st.as<float>(); float* stB = stA + Mp * S * 2;
   {
-    long long total = (long long)M * (E / 8);
+    long long total = (long long)Ml * (E / 8);
     HY3D_PROF(ctx, FAM_KV);
-    k_rows_to_t16_split<<<(unsigned)ceil_div64(total, 256), 256, 0, ctx->stream>>>(d_z, M, E, t.tz.as<uint8_t>());
+    k_rows_to_t16_split<<<(unsigned)ceil_div64(total, 256), 256, 0, ctx->stream>>>(d_z_local, Ml, E, t.tz.as<uint8_t>());
     HY3D_LAUNCH_CHECK(ctx);
   }
   GemmTC g{};
   g.Mb = Mb; g.A = t.tz.as<uint8_t>(); g.B = t.t_postkl; g.KB = 3 * E / 64; g.N = W; g.Nb = W / BN; g.bias = t.b_postkl;
-  g.Rout = x; g.Tcopy = ta; g.split_out = 1; g.st_out = stA; g.st_k = 2;
-  if (int rc = launch_gemm<EPI_X0>(ctx, g, FAM_KV)) return rc;
-  for (int l = 0; l < t.L; ++l) {
-    g = GemmTC{}; g.Mb = Mb;                                   // q, k, v = split(c_qkv(ln_1 x)), q/k norms
-    g.A = ta; g.B = t.t_qkv[l]; g.KB = 3 * W / 64; g.N = 3 * W; g.Nb = 3 * W / BN; g.bias = t.bb_qkv[l];
-    g.st_in = stA; g.st_slots = S; g.st_np = ST_COLS; g.cs = t.cs_qkv[l]; g.ln_eps = 1e-6f;
-    g.Tout = tq; g.Kout = t.kt.as<uint8_t>(); g.Vout = t.vt.as<uint8_t>(); g.nkv = Mb; g.Wq = W;
-    g.qn_w = t.qn_w[l]; g.qn_b = t.qn_b[l]; g.kn_w = t.kn_w[l]; g.kn_b = t.kn_b[l]; g.qk_norm = t.qk_norm;
-    g.qscale = rsqrtf(64.f) * LOG2E;
-    if (int rc = launch_gemm<EPI_QKV>(ctx, g, FAM_KV)) return rc;
-    {
-      AttnTC a{};
-      a.Q = tq; a.O = to; a.Pb = Mb; a.H = H; a.K = t.kt.as<uint8_t>(); a.V = t.vt.as<uint8_t>(); a.nkv = Mb; a.ntok = M; a.split_out = 1;
-      if (int rc = launch_attn(ctx, a, t.attn_fast[l] != 0, FAM_KV)) return rc;
-    }
-    g = GemmTC{}; g.Mb = Mb;                                   // x += c_proj(attn)
-    g.A = to; g.B = t.t_proj[l]; g.KB = 3 * W / 64; g.N = W; g.Nb = W / BN; g.bias = t.b_proj[l];
-    g.Rin = x; g.Rout = x; g.Tcopy = ta; g.split_out = 1; g.st_out = stB; g.st_k = 2;
-    if (int rc = launch_gemm<EPI_RES>(ctx, g, FAM_KV)) return rc;
-    g = GemmTC{}; g.Mb = Mb;                                   // h = gelu(c_fc(ln_2 x))
-    g.A = ta; g.B = t.t_fc[l]; g.KB = 3 * W / 64; g.N = R * W; g.Nb = R * W / BN; g.bias = t.bb_fc[l];
-    g.st_in = stB; g.st_slots = S; g.st_np = ST_COLS; g.cs = t.cs_fc[l]; g.ln_eps = 1e-6f; g.Tout = th; g.split_out = 1;
-    if (int rc = launch_gemm<EPI_GELU>(ctx, g, FAM_KV)) return rc;
-    g = GemmTC{}; g.Mb = Mb;                                   // x += c_proj(h)
-    g.A = th; g.B = t.t_proj2[l]; g.KB = 3 * R * W / 64; g.N = W; g.Nb = W / BN; g.bias = t.b_proj2[l];
-    g.Rin = x; g.Rout = x; g.Tcopy = ta; g.split_out = 1; g.st_out = stA; g.st_k = 2;
-    if (int rc = launch_gemm<EPI_RES>(ctx, g, FAM_KV)) return rc;
-  }
+  g.Rout = t.x.as<float>(); g.Tcopy = t.ta.as<uint8_t>(); g.split_out = 1; g.st_out = t.st.as<float>(); g.st_k = 2;
+  return launch_gemm<EPI_X0>(ctx, g, FAM_KV);
+}
+
+extern "C" int hy3d_transformer_layer_kv(hy3d_ctx* ctx, int32_t l, void* d_kv_all) {
+  if (!ctx || !d_kv_all) return HY3D_ERR_ARG;
+  TransformerState& t = ctx->tf;
+  if (!t.set || t.Ml <= 0 || l < 0 || l >= t.L) return hy3d_fail(ctx, HY3D_ERR_STATE, "hy3d_transformer_begin has not been called / bad layer");
+  const int W = t.W, Mb = t.Ml / 128, S = ST_PER_TILE * (W / BN);
+  float* stA = t.st.as<float>();
+  uint8_t* chunk = static_cast<uint8_t*>(d_kv_all) + (size_t)t.part * tf_chunk_bytes(t);
+  GemmTC g{}; g.Mb = Mb;                                       // q, k, v = split(c_qkv(ln_1 x)), q/k norms
+  g.A = t.ta.as<uint8_t>(); g.B = t.t_qkv[l]; g.KB = 3 * W / 64; g.N = 3 * W; g.Nb = 3 * W / BN; g.bias = t.bb_qkv[l];
+  g.st_in = stA; g.st_slots = S; g.st_np = ST_COLS; g.cs = t.cs_qkv[l]; g.ln_eps = 1e-6f;
+  g.Tout = t.tq.as<uint8_t>(); g.Kout = chunk; g.Vout = chunk + (size_t)t.H * Mb * TILE_BYTES; g.nkv = Mb; g.Wq = W;
+  g.qn_w = t.qn_w[l]; g.qn_b = t.qn_b[l]; g.kn_w = t.kn_w[l]; g.kn_b = t.kn_b[l]; g.qk_norm = t.qk_norm;
+  g.qscale = rsqrtf(64.f) * LOG2E;
+  return launch_gemm<EPI_QKV>(ctx, g, FAM_KV);
+}
+
+extern "C" int hy3d_transformer_layer_rest(hy3d_ctx* ctx, int32_t l, const void* d_kv_all) {
+  if (!ctx || !d_kv_all) return HY3D_ERR_ARG;
+  TransformerState& t = ctx->tf;
+  if (!t.set || t.Ml <= 0 || l < 0 || l >= t.L) return hy3d_fail(ctx, HY3D_ERR_STATE, "hy3d_transformer_begin has not been called / bad layer");
+  const int W = t.W, H = t.H, R = t.R, Mb = t.Ml / 128, S = ST_PER_TILE * (W / BN);
+  float* x = t.x.as<float>();
+  uint8_t *ta = t.ta.as<uint8_t>(), *to = t.to.as<uint8_t>(), *th = t.th.as<uint8_t>();
+  float* stA = t.st.as<float>(); float* stB = stA + (size_t)t.Ml * S * 2;
   {
-    long long total = (long long)M * (W / 4);
-    HY3D_PROF(ctx, FAM_KV);
-    k_r32_to_rows<<<(unsigned)ceil_div64(total, 256), 256, 0, ctx->stream>>>(x, M, W, d_out);
-    HY3D_LAUNCH_CHECK(ctx);
+    AttnTC a{};                                                // local query tiles against the K / V of ALL parts
+    a.Q = t.tq.as<uint8_t>(); a.O = to; a.Pb = Mb; a.H = H; a.split_out = 1;
+    a.K = static_cast<const uint8_t*>(d_kv_all); a.V = a.K + (size_t)H * Mb * TILE_BYTES;
+    a.nkv = Mb * t.parts; a.ntok = t.Ml * t.parts; a.kv_tpr = Mb; a.kv_chunk_stride = (long long)tf_chunk_bytes(t);
+    if (int rc = launch_attn(ctx, a, t.attn_fast[l] != 0, FAM_KV)) return rc;
   }
+  GemmTC g{}; g.Mb = Mb;                                       // x += c_proj(attn)
+  g.A = to; g.B = t.t_proj[l]; g.KB = 3 * W / 64; g.N = W; g.Nb = W / BN; g.bias = t.b_proj[l];
+  g.Rin = x; g.Rout = x; g.Tcopy = ta; g.split_out = 1; g.st_out = stB; g.st_k = 2;
+  if (int rc = launch_gemm<EPI_RES>(ctx, g, FAM_KV)) return rc;
+  g = GemmTC{}; g.Mb = Mb;                                     // h = gelu(c_fc(ln_2 x))
+  g.A = ta; g.B = t.t_fc[l]; g.KB = 3 * W / 64; g.N = R * W; g.Nb = R * W / BN; g.bias = t.bb_fc[l];
+  g.st_in = stB; g.st_slots = S; g.st_np = ST_COLS; g.cs = t.cs_fc[l]; g.ln_eps = 1e-6f; g.Tout = th; g.split_out = 1;
+  if (int rc = launch_gemm<EPI_GELU>(ctx, g, FAM_KV)) return rc;
+  g = GemmTC{}; g.Mb = Mb;                                     // x += c_proj(h)
+  g.A = th; g.B = t.t_proj2[l]; g.KB = 3 * R * W / 64; g.N = W; g.Nb = W / BN; g.bias = t.b_proj2[l];
+  g.Rin = x; g.Rout = x; g.Tcopy = ta; g.split_out = 1; g.st_out = stA; g.st_k = 2;
+  return launch_gemm<EPI_RES>(ctx, g, FAM_KV);
+}
+
+extern "C" int hy3d_transformer_end(hy3d_ctx* ctx, float* d_out_local) {
+  if (!ctx || !d_out_local) return HY3D_ERR_ARG;
+  TransformerState& t = ctx->tf;
+  if (!t.set || t.Ml <= 0) return hy3d_fail(ctx, HY3D_ERR_STATE, "hy3d_transformer_begin has not been called");
+  long long total = (long long)t.Ml * (t.W / 4);
+  HY3D_PROF(ctx, FAM_KV);
+  k_r32_to_rows<<<(unsigned)ceil_div64(total, 256), 256, 0, ctx->stream>>>(t.x.as<float>(), t.Ml, t.W, d_out_local);
+  HY3D_LAUNCH_CHECK(ctx);
   return HY3D_OK;
+}
+
+extern "C" int hy3d_transformer_forward(hy3d_ctx* ctx, const float* d_z, int32_t M, float* d_out) {
+  if (!ctx || !d_z || !d_out || M <= 0) return HY3D_ERR_ARG;
+  TransformerState& t = ctx->tf;
+  if (!t.set) return hy3d_fail(ctx, HY3D_ERR_STATE, "transformer weights not set");
+  if (int rc = hy3d_transformer_begin(ctx, d_z, M, 1, 0)) return rc;
+  HY3D_CUDA(ctx, t.kt.reserve(tf_chunk_bytes(t)));            // one part: the exchange buffer is private
+  for (int l = 0; l < t.L; ++l) {
+    if (int rc = hy3d_transformer_layer_kv(ctx, l, t.kt.p)) return rc;
+    if (int rc = hy3d_transformer_layer_rest(ctx, l, t.kt.p)) return rc;
+  }
+  return hy3d_transformer_end(ctx, d_out);
 }
 
 extern "C" int hy3d_debug_timers(hy3d_ctx* ctx, uint64_t h_out[32]) {

@@ -273,6 +273,11 @@ __device__ __forceinline__ uint64_t sub_f2(uint64_t a, uint64_t b) {
   asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
   return r;
 }
+__device__ __forceinline__ uint64_t mul_f2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
 __device__ __forceinline__ uint64_t fma_f2(uint64_t a, uint64_t b, uint64_t c) {
   uint64_t r;
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));

@@ -66,13 +66,16 @@ class B200ShapeVAE:
                 and c.embed_dim % 64 == 0 and c.num_decoder_layers > 0)
 
     @torch.no_grad()
-    def forward(self, latents: torch.Tensor, dtype=torch.float32, impl: str = None) -> torch.Tensor:
+    def forward(self, latents: torch.Tensor, dtype=torch.float32, impl: str = None, group=None) -> torch.Tensor:
         """ShapeVAE.forward (reference model.py:186-189): post_kl + Transformer.
 
         impl='tc' (the default and the product path): hand-written tcgen05 kernels of libhy3dgeo.so
         (``hy3d_transformer_forward``: 3-term split fp16 GEMMs = fp32-grade, LayerNorms folded, fp16
         self-attention), float32 result.  Shapes those kernels do not tile (head dim != 64, width not a multiple
         of 256, token count not a multiple of 128) raise — there is no silent library fallback.
+        ``group`` (a torch.distributed process group, or True for the default group): the latents are known on every rank
+        and the pass runs sequence-parallel over the group (hy3dgeo.h: hy3d_transformer_begin / layer_kv / layer_rest / end);
+        every rank gets the full result.
         impl='torch' must be asked for explicitly: the same network on cuBLAS + SDPA library ops in ``dtype``, kept
         as a cross-check for the parity tests (47 ms in fp32 for 3072 tokens vs ~5 ms)."""
         if impl is None:
@@ -89,6 +92,15 @@ class B200ShapeVAE:
             ctx = get_context(self.device)
             ctx.set_transformer(self.sd, self.cfg, key=id(self.sd), owner=self)
             z = latents.to(self.device)
+            if group is not None:
+                # sequence parallel over a process group: each rank runs M / world token rows, the K / V tile images are
+                # all-gathered once per layer (what a rank repeats for every latent does not shrink with more GPUs otherwise)
+                import torch.distributed as dist
+                world = dist.get_world_size(group if group is not True else None)
+                if world > 1 and z.shape[-2] % (128 * world) == 0:
+                    g = None if group is True else group
+                    return torch.stack([ctx.transformer_forward_parallel(z[b], self.cfg.heads, self.cfg.num_decoder_layers, g)
+                                        for b in range(z.shape[0])], 0)
             return torch.stack([ctx.transformer_forward(z[b]) for b in range(z.shape[0])], 0)
         return self._forward_torch(latents, dtype)
 

@@ -354,19 +354,32 @@ class ShardedHierarchicalVolumeDecoding:
     Coarse levels: every rank evaluates its share (level 0: an axis-0 slab; refined levels: an equal contiguous range
     of the ordered active list), the values are all-gathered and every rank holds the whole level — the next active
     set is derived identically everywhere from it.
-    Last level (``keep_sharded``, default): the active list is cut at plane boundaries into runs of near-equal length;
-    each rank evaluates the queries of its planes plus those of the next two planes (its marching-cubes halo, < 1 %
-    extra work at octree 384 on 8 GPUs), fills only its own slab and returns a ``SlabGrid`` — no all-gather of the
-    values, no full-resolution grid anywhere; the mesh is then extracted slab by slab.  With ``keep_sharded=False`` the
+    Last level (``keep_sharded``, default): the grid is cut at plane boundaries into slabs holding near-equal numbers of
+    active voxels; the decoder work is split into exactly equal ranges of the ordered list, and the values that fall
+    into another rank's slab (or its two-plane marching-cubes halo) change hands in one batched point-to-point exchange
+    (a few % of the list).  Each rank fills only its own slab and returns a ``SlabGrid`` — no all-gather of the values, no
+    full-resolution grid anywhere; the mesh is then extracted slab by slab.  With ``keep_sharded=False`` the
     last level is gathered like the others and the ordinary tensor is returned on all ranks."""
 
-    def __init__(self, group=None, keep_sharded: bool = True):
+    def __init__(self, group=None, keep_sharded: bool = True, timeline: bool = False):
         self.group = group
         self.keep_sharded = keep_sharded
+        self.timeline = {} if timeline else None      # diagnostics: stage -> accumulated ms (synchronising; tools/gpu_hier_timeline.py)
+
+    def _tick(self, name, dev):
+        if self.timeline is None:
+            return
+        import time
+        torch.cuda.synchronize(dev)
+        now = time.perf_counter()
+        if getattr(self, "_t_last", None) is not None and name:
+            self.timeline[name] = self.timeline.get(name, 0.0) + (now - self._t_last) * 1e3
+        self._t_last = now
 
     @torch.no_grad()
     def __call__(self, latents, geo_decoder, bounds=1.01, num_chunks=10000, mc_level=0.0, octree_resolution=None,
                  min_resolution=63, enable_pbar=True, **kwargs):
+        self._tick(None, latents.device)
         ctx = bind(latents, geo_decoder)
         levels = hierarchy_levels(octree_resolution, min_resolution)
         b6 = normalize_bounds(bounds)
@@ -378,30 +391,57 @@ class ShardedHierarchicalVolumeDecoding:
         self.last_stats = []
         for b in range(latents.shape[0]):
             ctx.prepare_kv(latents[b])
+            self._tick("kv_prepare", latents.device)
             n0 = levels[0] + 1
             ax = axis_tables(bounds, levels[0])
             grid = decode_dense_sharded(lambda first, count, out: ctx.decode_dense(ax, first, count, out), (n0, n0, n0),
                                         latents.device, self.group, to_all=True).contiguous()
+            self._tick("level0 decode + all_gather", latents.device)
             queries, mine = [n0 ** 3], [(slab_planes(n0, rank, world)[1] - slab_planes(n0, rank, world)[0]) * n0 * n0]
             for r in levels[1:]:
                 n = r + 1
                 last = r == levels[-1]
                 index = refine_level(ctx, grid, mc_level, last=last, nf=n)
+                self._tick(f"refine -> {n}^3 (replicated)", latents.device)
                 cell = (bbox_size / r).astype(np.float32)
                 queries.append(int(index.numel()))
                 if last and sharded_last:
                     planes, starts, ends = plane_cuts(index, n, world)
+                    self._tick("plane cuts", latents.device)
                     plane0, own = planes[rank], planes[rank + 1] - planes[rank]
                     p_hi = min(planes[rank + 1] + MC_HALO, n)
-                    part = index[starts[rank]: ends[rank]]
+                    lo, hi = starts[rank], ends[rank]             # list entries whose values this rank's slab (+ halo) needs
+                    # decoder work is split into EQUAL ranges of the list (plane-aligned slabs differ by up to +-8 % in
+                    # queries at octree 384 on 8 GPUs); the few values that fall into a neighbour's slab change hands
+                    # in one batched point-to-point exchange (every rank knows all the boundaries)
+                    cnt = int(index.numel())
+                    rng = [list_range(cnt, q, world) for q in range(world)]
+                    a, bq = rng[rank]
+                    vals = ctx.decode_list_values(index[a:bq], (n, n, n), cell, bmin32) if bq > a else \
+                        torch.empty(0, dtype=torch.float32, device=latents.device)
+                    need = torch.empty(hi - lo, dtype=torch.float32, device=latents.device)
+                    sends, recvs = [], []
+                    for q in range(world):
+                        s0, s1 = max(a, starts[q]), min(bq, ends[q])          # mine, needed by q
+                        r0, r1 = max(rng[q][0], lo), min(rng[q][1], hi)       # q's, needed by me
+                        if q == rank:
+                            if r1 > r0:
+                                need[r0 - lo: r1 - lo] = vals[r0 - a: r1 - a]
+                            continue
+                        if s1 > s0:
+                            sends.append((vals[s0 - a: s1 - a], q))
+                        if r1 > r0:
+                            recvs.append((need[r0 - lo: r1 - lo], q))
+                    _run_p2p(sends, recvs, self.group)
                     slab = torch.empty((p_hi - plane0, n, n), dtype=torch.float32, device=latents.device)
                     ctx.fill(slab, float("nan"))           # unvisited = NaN from the start: no sentinel sweep afterwards
-                    if part.numel():
-                        vals = ctx.decode_list_values(part, (n, n, n), cell, bmin32)
-                        ctx.scatter(part, vals, slab, base=plane0 * n * n)
+                    if hi > lo:
+                        ctx.scatter(index[lo:hi], need, slab, base=plane0 * n * n)
+                    part = index[a:bq]
                     grid = slab
                     plane0s.append(plane0); owns.append(own)
                     mine.append(int(part.numel()))
+                    self._tick("last level decode (own slab)", latents.device)
                     break
                 vals = decode_list_sharded(lambda idx: ctx.decode_list_values(idx, (n, n, n), cell, bmin32), index, self.group)
                 nxt = torch.empty((n, n, n), dtype=torch.float32, device=latents.device)
@@ -410,6 +450,7 @@ class ShardedHierarchicalVolumeDecoding:
                 grid = nxt
                 a, bb = list_range(index.numel(), rank, world)
                 mine.append(bb - a)
+                self._tick(f"level {n}^3 decode + all_gather + scatter", latents.device)
             if not sharded_last:
                 ctx.sentinel_to_nan(grid, SENTINEL)
             outs.append(grid)

@@ -105,6 +105,19 @@ int hy3d_set_transformer_weights(hy3d_ctx* ctx, const hy3d_transformer_desc* des
 /* d_z: fp32 [M, embed_dim] (already divided by scale_factor, pipelines.py:657); d_out: fp32 [M, W]. M % 128 == 0. */
 int hy3d_transformer_forward(hy3d_ctx* ctx, const float* d_z, int32_t M, float* d_out);
 
+/* Sequence-parallel form of the same forward pass (no reference counterpart: the reference is single-device).
+ * The M tokens of a latent set are split into `parts` equal ranges (M / parts a multiple of 128), one per GPU; every GEMM,
+ * LayerNorm and residual acts on rows, only self-attention needs all tokens' K / V.  Per layer the host runs
+ *   hy3d_transformer_layer_kv   -> this part's K / V^T tile images into chunk `part` of the exchange buffer,
+ *   [all-gather of the chunks across the GPUs — NCCL, done by the caller; in place],
+ *   hy3d_transformer_layer_rest -> attention of the local queries against all K / V, c_proj, MLP.
+ * Exchange buffer (DEVICE, caller-owned): [parts][2 (K, V^T)][heads][M / parts / 128][16 KB] bytes.
+ * hy3d_transformer_forward is exactly begin(parts = 1) + the layer loop on a private buffer + end. */
+int hy3d_transformer_begin(hy3d_ctx* ctx, const float* d_z_local, int32_t tokens_local, int32_t parts, int32_t part);
+int hy3d_transformer_layer_kv(hy3d_ctx* ctx, int32_t layer, void* d_kv_all);
+int hy3d_transformer_layer_rest(hy3d_ctx* ctx, int32_t layer, const void* d_kv_all);
+int hy3d_transformer_end(hy3d_ctx* ctx, float* d_out_local);
+
 /* ---- decoder: replaces CrossAttentionDecoder.forward (attention_blocks.py:483-493) ---- */
 /* Copies / re-lays-out the weights into the context (fp16 UMMA tiles + fp32 originals). */
 int hy3d_set_decoder_weights(hy3d_ctx* ctx, const hy3d_decoder_desc* desc);

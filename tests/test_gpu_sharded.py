@@ -44,6 +44,10 @@ def _worker(rank, world, port, q):
         z = W.synthetic_latents(cfg, 3, 1234).to(dev)
         lat = P.broadcast_latents(vae(z) if rank == 0 else None, (3, cfg.num_latents, cfg.width), dev)
         ctx = _lib.get_context(dev)
+        # ---- latent transformer, sequence parallel (token ranges per rank, K / V tiles all-gathered per layer): bit-identical
+        lat_sp = vae(z[:2], group=True)
+        if not _same(lat_sp, vae(z[:2])):
+            raise AssertionError("sequence-parallel latent transformer differs from the single-GPU pass")
         ext = MCSurfaceExtractor()
         fails = []
 
