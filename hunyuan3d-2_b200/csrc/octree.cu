@@ -1,109 +1,131 @@
 // Coarse-to-fine octree refinement: replaces extract_near_surface_volume_fn + the Conv3d
 // dilations + torch.where of the reference (volume_decoders.py:29-119, :245-260, :376-391;
-// restated in SURVEY App. B).  All integer/byte work, HBM/L2-bound: no float grids, no host
-// round trips except the final count.
+// restated in SURVEY App. B).  All integer/bit work, HBM/L2-bound: the coarse grid is read once, everything after that
+// happens on bit rows (1 bit per voxel, rows padded to 32-bit words), no float grids, no byte masks, no host round trips
+// except the final count.
 //
-//   coarse grid G[n^3] --k_coarse_active--> act (u8) --[k_dilate3 if not last]-->
-//   fine mask evaluated on the fly from act (the x2 up-sampling followed by 1 or 2 box
-//   dilations collapses to "any active coarse voxel c with |2c - f|_inf <= r", r = 1 or 2)
-//   --k_fine_ballot--> bit words + per-block counts --k_scan--> offsets
-//   --k_fine_emit--> ordered flat indices (torch.where order)
+//   coarse grid G[n^3] --k_coarse_bits--> act bits [n*n rows][ceil(n/32)]                     (near-surface | band mask)
+//   [not last level]   --k_dilate_bits--> 3x3x3 box dilation in bit space (word-parallel shifts / ORs of 9 rows)
+//   fine mask: the x2 up-sampling followed by 1 or 2 box dilations collapses to "any active coarse voxel c with
+//   |2c - f|_inf <= r" (r = 1 or 2).  Along k that is, for a whole 32-voxel fine word at once,
+//       even f = 2m: a[m] (r = 1) or a[m-1] | a[m] | a[m+1] (r = 2);   odd f = 2m+1: a[m] | a[m+1]
+//   on the 18 coarse bits under the word, bit-interleaved back to 32 fine bits; along i and j the same rule picks 1-3
+//   coarse rows per axis, OR-ed before the k rule.                --k_fine_words--> fine bits [nf*nf rows][ceil(nf/32)]
+//   --k_scan_i32--> offsets of 256-word blocks --k_words_emit--> ordered flat indices (torch.where order)
 #include "common.cuh"
 
 namespace {
 
 __device__ __forceinline__ int sgn(float v) { return (v > 0.f) - (v < 0.f); }
 
-__global__ void k_coarse_active(const float* __restrict__ g, int n, float alpha, uint8_t* __restrict__ act) {
-  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long total = (long long)n * n * n;
-  if (t >= total) return;
-  const unsigned tu = (unsigned)t;                       // grids are < 2^31 voxels: 32-bit index arithmetic
-  int k = tu % n; unsigned r = tu / n; int j = r % n; int i = r / n;
-  float gv = g[t];
-  float val = __fadd_rn(gv, alpha);
-  bool valid = val > -9000.f;
-  int s = sgn(val);
-  bool diff = false;
-  const long long sn[3] = {(long long)n * n, n, 1};
-  const int idx[3] = {i, j, k};
+// one block per coarse row (i, j), one thread per k (blockDim = 32 * words per row): 1 bit per voxel
+__global__ void k_coarse_bits(const float* __restrict__ g, int n, int wpr, float alpha, uint32_t* __restrict__ act) {
+  const int row = blockIdx.x, i = row / n, j = row - i * n, k = threadIdx.x;
+  bool on = false;
+  if (k < n) {
+    const long long t = (long long)row * n + k;
+    const float gv = g[t];
+    const float val = __fadd_rn(gv, alpha);
+    const bool valid = val > -9000.f;
+    const int s = sgn(val);
+    bool diff = false;
+    const long long sn[3] = {(long long)n * n, n, 1};
+    const int idx[3] = {i, j, k};
 #pragma unroll
-  for (int a = 0; a < 3; ++a) {
+    for (int a = 0; a < 3; ++a) {
 #pragma unroll
-    for (int d = -1; d <= 1; d += 2) {
-      int c = idx[a] + d;
-      c = c < 0 ? 0 : (c > n - 1 ? n - 1 : c);                 // replicate padding
-      float nb = __fadd_rn(g[t + (long long)(c - idx[a]) * sn[a]], alpha);
-      if (!(nb > -9000.f)) nb = val;                           // invalid neighbour -> own value
-      diff |= sgn(nb) != s;
+      for (int d = -1; d <= 1; d += 2) {
+        int c = idx[a] + d;
+        c = c < 0 ? 0 : (c > n - 1 ? n - 1 : c);                 // replicate padding
+        float nb = __fadd_rn(g[t + (long long)(c - idx[a]) * sn[a]], alpha);
+        if (!(nb > -9000.f)) nb = val;                           // invalid neighbour -> own value
+        diff |= sgn(nb) != s;
+      }
     }
+    on = (diff && valid) || (fabsf(gv) < HY3D_BAND);
   }
-  act[t] = (uint8_t)((diff && valid) || (fabsf(gv) < HY3D_BAND));
+  const uint32_t m = __ballot_sync(0xffffffffu, on);
+  if ((threadIdx.x & 31) == 0) act[(size_t)row * wpr + (threadIdx.x >> 5)] = m;
 }
 
-__global__ void k_dilate3(const uint8_t* __restrict__ in, int n, uint8_t* __restrict__ out) {
-  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long total = (long long)n * n * n;
-  if (t >= total) return;
-  const unsigned tu = (unsigned)t;
-  int k = tu % n; unsigned r = tu / n; int j = r % n; int i = r / n;
-  uint8_t v = 0;
+// 3x3x3 box dilation on bit rows (zero beyond the grid): thread per (row, word)
+__global__ void k_dilate_bits(const uint32_t* __restrict__ in, int n, int wpr, uint32_t* __restrict__ out) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)n * n * wpr) return;
+  const int w = (int)(t % wpr); const int row = (int)(t / wpr); const int i = row / n, j = row - i * n;
+  uint32_t x = 0, l = 0, r = 0;
   for (int a = max(i - 1, 0); a <= min(i + 1, n - 1); ++a)
-    for (int b = max(j - 1, 0); b <= min(j + 1, n - 1); ++b)
-      for (int c = max(k - 1, 0); c <= min(k + 1, n - 1); ++c) v |= in[((long long)a * n + b) * n + c];
-  out[t] = v;
-}
-
-__device__ __forceinline__ bool fine_active(const uint8_t* __restrict__ act, int n, int reach, int fi, int fj, int fk) {
-  // coarse c with |2c - f| <= reach  <=>  ceil((f-reach)/2) <= c <= floor((f+reach)/2)
-  int lo[3], hi[3];
-  const int f[3] = {fi, fj, fk};
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    int l = f[a] - reach, h = f[a] + reach;
-    lo[a] = l <= 0 ? 0 : (l + 1) >> 1;
-    hi[a] = h >> 1;
-    if (hi[a] > n - 1) hi[a] = n - 1;
-  }
-  for (int a = lo[0]; a <= hi[0]; ++a)
-    for (int b = lo[1]; b <= hi[1]; ++b)
-      for (int c = lo[2]; c <= hi[2]; ++c)
-        if (act[((long long)a * n + b) * n + c]) return true;
-  return false;
-}
-
-constexpr int FB_WARPS = 8;
-constexpr int FB_ITERS = 16;                      // 32-voxel words per warp
-constexpr int FB_BLOCK = FB_WARPS * FB_ITERS * 32;  // 4096 fine voxels per block
-
-// cand = 3x3x3 dilation of act: if cand[f >> 1] is clear no coarse voxel within reach of f is active
-// (all candidates lie in [f>>1 - 1, f>>1 + 1] per axis), so most fine voxels cost one byte load.
-__global__ void __launch_bounds__(FB_WARPS * 32) k_fine_ballot(const uint8_t* __restrict__ act, const uint8_t* __restrict__ cand,
-                                                                int n, int nf, int reach, uint32_t* __restrict__ words,
-                                                                int* __restrict__ blockcnt) {
-  __shared__ int wc[FB_WARPS];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long total = (long long)nf * nf * nf;
-  long long base = (long long)blockIdx.x * FB_BLOCK + (long long)warp * FB_ITERS * 32;
-  int cnt = 0;
-  for (int it = 0; it < FB_ITERS; ++it) {
-    long long t = base + it * 32 + lane;
-    bool on = false;
-    if (t < total) {
-      const unsigned tu = (unsigned)t;
-      int k = tu % nf; unsigned r = tu / nf; int j = r % nf; int i = r / nf;
-      if (cand[((long long)(i >> 1) * n + (j >> 1)) * n + (k >> 1)]) on = fine_active(act, n, reach, i, j, k);
+    for (int b = max(j - 1, 0); b <= min(j + 1, n - 1); ++b) {
+      const uint32_t* p = in + ((size_t)a * n + b) * wpr;
+      x |= p[w];
+      if (w > 0) l |= p[w - 1];
+      if (w + 1 < wpr) r |= p[w + 1];
     }
-    uint32_t m = __ballot_sync(0xffffffffu, on);
-    if (lane == 0 && base + it * 32 < total) words[(base >> 5) + it] = m;
-    cnt += __popc(m);
+  uint32_t d = x | (x << 1) | (x >> 1) | (l >> 31) | (r << 31);
+  const int valid = n - w * 32;
+  if (valid < 32) d &= (1u << valid) - 1u;
+  out[t] = d;
+}
+
+__device__ __forceinline__ uint32_t spread16(uint32_t x) {      // bit s of x -> bit 2s
+  x &= 0xFFFFu;
+  x = (x | (x << 8)) & 0x00FF00FFu;
+  x = (x | (x << 4)) & 0x0F0F0F0Fu;
+  x = (x | (x << 2)) & 0x33333333u;
+  x = (x | (x << 1)) & 0x55555555u;
+  return x;
+}
+
+constexpr int FW_BLOCK = 256;                      // fine words per block (= per scan element)
+
+// thread per fine word (fine row (fi, fj), word w): 32 fine voxels from the 18 coarse bits under them, OR-ed over the
+// coarse rows within reach in i and j.  Also the block's population count for the ordered compaction.
+__global__ void __launch_bounds__(FW_BLOCK) k_fine_words(const uint32_t* __restrict__ act, int n, int wpr_c, int nf, int wpr_f,
+                                                          int reach, long long nwords, uint32_t* __restrict__ words,
+                                                          int* __restrict__ blockcnt) {
+  const long long L = (long long)blockIdx.x * FW_BLOCK + threadIdx.x;
+  uint32_t out = 0;
+  if (L < nwords) {
+    const int w = (int)(L % wpr_f); const int row = (int)(L / wpr_f); const int fi = row / nf, fj = row - fi * nf;
+    // coarse index range per axis: ceil((f - reach) / 2) .. floor((f + reach) / 2), clipped
+    int lo[2], hi[2];
+    const int f2[2] = {fi, fj};
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int l = f2[a] - reach, h = f2[a] + reach;
+      lo[a] = l <= 0 ? 0 : (l + 1) >> 1;
+      hi[a] = min(h >> 1, n - 1);
+    }
+    const int start = 16 * w - 1;                  // window bit t <-> coarse k = start + t, t = 0 .. 17
+    uint32_t a18 = 0;
+    for (int ci = lo[0]; ci <= hi[0]; ++ci)
+      for (int cj = lo[1]; cj <= hi[1]; ++cj) {
+        const uint32_t* p = act + ((size_t)ci * n + cj) * wpr_c;
+        uint32_t win;
+        if (start < 0) win = p[0] << 1;
+        else {
+          const int idx = start >> 5, sh = start & 31;
+          const uint32_t w0 = p[idx], w1 = idx + 1 < wpr_c ? p[idx + 1] : 0u;
+          win = __funnelshift_r(w0, w1, sh);
+        }
+        a18 |= win;
+      }
+    const uint32_t e = reach == 2 ? (a18 | (a18 >> 1) | (a18 >> 2)) : (a18 >> 1);      // even fine voxels 2m (m = 16 w + s)
+    const uint32_t o = (a18 >> 1) | (a18 >> 2);                                         // odd fine voxels 2m + 1
+    out = spread16(e) | (spread16(o) << 1);
+    const int valid = nf - w * 32;
+    if (valid < 32) out &= (1u << valid) - 1u;
+    words[L] = out;
   }
-  if (lane == 0) wc[warp] = cnt;
+  int c = __popc(out);
+  __shared__ int red[FW_BLOCK / 32];
+  for (int s = 16; s; s >>= 1) c += __shfl_xor_sync(0xffffffffu, c, s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c;
   __syncthreads();
   if (threadIdx.x == 0) {
-    int s = 0;
-    for (int w = 0; w < FB_WARPS; ++w) s += wc[w];
-    blockcnt[blockIdx.x] = s;
+    int t = 0;
+    for (int q = 0; q < FW_BLOCK / 32; ++q) t += red[q];
+    blockcnt[blockIdx.x] = t;
   }
 }
 
@@ -128,26 +150,32 @@ __global__ void __launch_bounds__(1024) k_scan_i32(const int* __restrict__ in, i
   if (tid == 1023) out[n] = part[1023];
 }
 
-__global__ void __launch_bounds__(FB_WARPS * 32) k_fine_emit(const uint32_t* __restrict__ words, long long nwords,
-                                                              const long long* __restrict__ blockoff, int32_t* __restrict__ index,
-                                                              long long cap) {
-  __shared__ int wc[FB_WARPS];
+// ordered compaction of the row-aligned fine words: warp = 32 consecutive words (lane holds one), every set bit becomes
+// the flat index (row * nf + 32 w + bit) at its rank — coalesced stores, no atomics
+__global__ void __launch_bounds__(FW_BLOCK) k_words_emit(const uint32_t* __restrict__ words, long long nwords, int nf, int wpr_f,
+                                                          const long long* __restrict__ blockoff, int32_t* __restrict__ index,
+                                                          long long cap) {
+  __shared__ int wc[FW_BLOCK / 32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long w0 = (long long)blockIdx.x * (FB_BLOCK / 32) + (long long)warp * FB_ITERS;
-  uint32_t my = (lane < FB_ITERS && w0 + lane < nwords) ? words[w0 + lane] : 0u;
+  const long long L = (long long)blockIdx.x * FW_BLOCK + threadIdx.x;
+  const uint32_t my = L < nwords ? words[L] : 0u;
   int c = __popc(my), incl = c;
   for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
   if (lane == 31) wc[warp] = incl;
   __syncthreads();
   long long off = blockoff[blockIdx.x];
-  for (int w = 0; w < warp; ++w) off += wc[w];
-  int excl = incl - c;
-  for (int it = 0; it < FB_ITERS; ++it) {
-    uint32_t m = __shfl_sync(0xffffffffu, my, it);
-    int e = __shfl_sync(0xffffffffu, excl, it);
+  for (int q = 0; q < warp; ++q) off += wc[q];
+  const int excl = incl - c;
+  const int row = (int)(L / wpr_f), w = (int)(L - (long long)row * wpr_f);
+  const int base = L < nwords ? row * nf + 32 * w : 0;          // flat index of this word's bit 0 (nf^3 < 2^31)
+  for (int it = 0; it < 32; ++it) {
+    const uint32_t m = __shfl_sync(0xffffffffu, my, it);
+    if (m == 0u) continue;                                       // (uniform)
+    const int e = __shfl_sync(0xffffffffu, excl, it);
+    const int b0 = __shfl_sync(0xffffffffu, base, it);
     if ((m >> lane) & 1u) {
-      long long pos = off + e + __popc(m & ((1u << lane) - 1u));
-      if (pos < cap) index[pos] = (int32_t)((w0 + it) * 32 + lane);
+      const long long pos = off + e + __popc(m & ((1u << lane) - 1u));
+      if (pos < cap) index[pos] = b0 + lane;
     }
   }
 }
@@ -187,43 +215,40 @@ int hy3d_refine_level(hy3d_ctx* ctx, const float* d_coarse, int32_t n, int32_t n
   // every up-sampled voxel 2c must exist (nf >= 2n - 1) and every fine voxel must have a coarse parent f >> 1 (nf <= 2n)
   if (nf < 2 * n - 1 || nf > 2 * n) return hy3d_fail(ctx, HY3D_ERR_ARG, "fine grid %d^3 does not refine a %d^3 grid (need 2n-1 or 2n)", nf, n);
   HY3D_CUDA(ctx, cudaSetDevice(ctx->device));
-  const long long nc = (long long)n * n * n;
   const long long nfine = (long long)nf * nf * nf;
   if (nfine > 2147483647LL) return hy3d_fail(ctx, HY3D_ERR_UNSUPPORTED, "fine grid too large for int32 indices");
-  const long long nwords = (nfine + 31) / 32;
-  const int nblocks = (int)ceil_div64(nfine, FB_BLOCK);
-  size_t need = (size_t)nc * 3 + 512;
-  HY3D_CUDA(ctx, ctx->scratch.reserve(need));
+  if (n > 1024) return hy3d_fail(ctx, HY3D_ERR_UNSUPPORTED, "coarse grids above 1024^3 are not supported");
+  const int wpr_c = (n + 31) / 32, wpr_f = (nf + 31) / 32;
+  const long long cwords = (long long)n * n * wpr_c;
+  const long long nwords = (long long)nf * nf * wpr_f;
+  const int nblocks = (int)ceil_div64(nwords, FW_BLOCK);
+  HY3D_CUDA(ctx, ctx->scratch.reserve((size_t)cwords * 4 * 2 + 512));
   HY3D_CUDA(ctx, ctx->scratch2.reserve((size_t)nwords * 4 + (size_t)nblocks * 4 + (size_t)(nblocks + 1) * 8 + 1024));
-  uint8_t* act = ctx->scratch.as<uint8_t>();
-  uint8_t* act2 = act + ((nc + 127) / 128 * 128);
-  uint8_t* cand = act2 + ((nc + 127) / 128 * 128);
+  uint32_t* act = ctx->scratch.as<uint32_t>();
+  uint32_t* act2 = act + ((cwords + 63) / 64 * 64);
   uint32_t* words = ctx->scratch2.as<uint32_t>();
   int* blockcnt = reinterpret_cast<int*>(words + ((nwords + 63) / 64 * 64));
   long long* blockoff = reinterpret_cast<long long*>(blockcnt + ((nblocks + 63) / 64 * 64));
   HY3D_PROF(ctx, FAM_OCTREE);
-  k_coarse_active<<<(unsigned)ceil_div64(nc, 256), 256, 0, ctx->stream>>>(d_coarse, n, mc_level, act);
+  k_coarse_bits<<<(unsigned)(n * n), wpr_c * 32, 0, ctx->stream>>>(d_coarse, n, wpr_c, mc_level, act);
   HY3D_LAUNCH_CHECK(ctx);
-  const uint8_t* mask = act;
+  const uint32_t* mask = act;
   if (!last_level) {
     HY3D_PROF(ctx, FAM_OCTREE);
-    k_dilate3<<<(unsigned)ceil_div64(nc, 256), 256, 0, ctx->stream>>>(act, n, act2);
+    k_dilate_bits<<<(unsigned)ceil_div64(cwords, 256), 256, 0, ctx->stream>>>(act, n, wpr_c, act2);
     HY3D_LAUNCH_CHECK(ctx);
     mask = act2;
   }
   const int reach = last_level ? 2 : 1;
   HY3D_PROF(ctx, FAM_OCTREE);
-  k_dilate3<<<(unsigned)ceil_div64(nc, 256), 256, 0, ctx->stream>>>(mask, n, cand);
-  HY3D_LAUNCH_CHECK(ctx);
-  HY3D_PROF(ctx, FAM_OCTREE);
-  k_fine_ballot<<<nblocks, FB_WARPS * 32, 0, ctx->stream>>>(mask, cand, n, nf, reach, words, blockcnt);
+  k_fine_words<<<nblocks, FW_BLOCK, 0, ctx->stream>>>(mask, n, wpr_c, nf, wpr_f, reach, nwords, words, blockcnt);
   HY3D_LAUNCH_CHECK(ctx);
   HY3D_PROF(ctx, FAM_OCTREE);
   k_scan_i32<<<1, 1024, 0, ctx->stream>>>(blockcnt, nblocks, blockoff);
   HY3D_LAUNCH_CHECK(ctx);
   if (cap > 0) {
     HY3D_PROF(ctx, FAM_OCTREE);
-    k_fine_emit<<<nblocks, FB_WARPS * 32, 0, ctx->stream>>>(words, nwords, blockoff, d_index, cap);
+    k_words_emit<<<nblocks, FW_BLOCK, 0, ctx->stream>>>(words, nwords, nf, wpr_f, blockoff, d_index, cap);
     HY3D_LAUNCH_CHECK(ctx);
   }
   long long* pinned = reinterpret_cast<long long*>(ctx->pinned);

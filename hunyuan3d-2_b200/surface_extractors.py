@@ -149,12 +149,27 @@ class MCSurfaceExtractor(SurfaceExtractor):
 
 
 class DMCSurfaceExtractor(SurfaceExtractor):
-    """reference :79-94 wraps ``diso.DiffDMC``; out of scope for this path (SURVEY §2 row 2,
-    §8f rank 4).  Kept in the registry so ``mc_algo='dmc'`` fails the way a missing
-    ``diso`` does in the reference: the item becomes ``None``."""
+    """Second entry of the ``mc_algo`` registry (reference :79-94): dual marching cubes through the third-party ``diso``
+    package (``diso.DiffDMC``, not vendored by the reference, absent from this image).  hy3dgeo does not re-implement it
+    (DESIGN.md §7): where ``diso`` is importable this class drives it exactly as the reference does —
+    ``sdf = -logits / octree_resolution``, ``normalize=True``, vertices re-centred on their bounding box, winding reversed —
+    and where it is not, ``run`` raises the reference's ImportError, so the item becomes ``None`` as it does there.
+    NaN voxels (sparse decoders) are passed through untouched, as in the reference."""
 
     def run(self, grid_logit, *, octree_resolution, **kwargs):
-        raise ImportError("DMCSurfaceExtractor is not provided by hy3dgeo; set mc_algo to 'mc'")
+        if type(grid_logit).__name__ == "SlabGrid":
+            grid_logit = grid_logit.to_tensor()[0]
+        if not hasattr(self, "dmc"):
+            try:
+                from diso import DiffDMC
+            except ImportError:
+                raise ImportError("Please install diso via `pip install diso`, or set mc_algo to 'mc'")
+            self.dmc = DiffDMC(dtype=torch.float32).to(grid_logit.device)
+        sdf = (-grid_logit / octree_resolution).to(torch.float32).contiguous()
+        verts, faces = self.dmc(sdf, deform=None, return_quads=False, normalize=True)
+        lo, hi = verts.min(dim=0)[0], verts.max(dim=0)[0]
+        verts = verts - 0.5 * (lo + hi)                       # center_vertices (:29-34)
+        return verts.detach().cpu().numpy(), faces.detach().cpu().numpy()[:, ::-1]
 
 
 def export_to_trimesh(mesh_output, device=None):
