@@ -47,6 +47,9 @@ struct DecoderWeights {
   const float *cs_q, *bb_q, *cs_fc, *bb_fc, *dotw, *c12;
   const __half *t_ckv3, *t_lp3;                           // c_kv (ln_2 folded, [k | v] rows) and latents_proj, 3-term split
   const float *cs_kv, *bb_kv;
+  const __half* t_cqx = nullptr;                         // c_q . query_proj collapsed into one K = 192 image (x0 never formed)
+  const float *qs_wbar = nullptr, *qs_hc = nullptr, *qs_Gc = nullptr, *qs_scal = nullptr;   // closed-form ln_1 statistics of x0
+  const float* cs_qx = nullptr;                          // exact column sums of the gamma-folded c_q weight (collapsed path)
   const __half* t_cpx; const float* b_cpx;               // [c_proj | query_proj] K-concatenated image and b_o + b_qp (fused residual)
   const __half* t_cq3;
   float attn_bound = 0.f;              // upper bound of |q.k| scale log2e from the q/k norm WEIGHTS alone (inf without qk_norm)

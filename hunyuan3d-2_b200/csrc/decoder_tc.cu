@@ -63,7 +63,7 @@ struct GemmTC {
   // so  LN(x) W^T = rstd * (x W'^T - mean * cs) + (beta W^T + bias);  row statistics come as S partial
   // (mean, M2) slots written by the producer's epilogue and are merged here (Chan et al.), deterministically.
   const float* st_in; int st_slots; int st_np; const float* cs; float ln_eps;
-  const float2* ln_mr;   // per row (mean, rstd) merged from st_in by k_finish_stats (set by launch_gemm)
+  const float2* ln_mr;   // per row (mean, rstd): merged from st_in by k_finish_stats (set by launch_gemm), or given directly
   // statistics of the rows this GEMM produces (EPI_X0 / EPI_RES): slot nb * 4 + column quarter <- (mean, M2[, dot with dotw]) of 64 columns
   float* st_out; int st_k; const float* dotw;
   uint8_t* Tcopy;        // fp16 T16 copy of the fp32 rows written to Rout (operand of the next GEMM)
@@ -304,7 +304,7 @@ k_gemm_tc(GemmTC g, const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const uint32_t tcol = tmem + acc * BN + cq * 64 + ((uint32_t)(q * 32) << 16);
       const int c0 = nb * BN + cq * 64;     // first global column of this warp's quarter
       float ln_mean = 0.f, ln_rstd = 1.f;
-      if (g.st_in) { const float2 mr = __ldg(g.ln_mr + (size_t)mb * TILE_M + r); ln_mean = mr.x; ln_rstd = mr.y; }
+      if (g.ln_mr) { const float2 mr = __ldg(g.ln_mr + (size_t)mb * TILE_M + r); ln_mean = mr.x; ln_rstd = mr.y; }
       const float nm = -ln_rstd * ln_mean;
       // 32 accumulator columns [c0 + 32 ch, +32) -> x: + bias, or the folded LayerNorm  rstd * a + (bb - rstd * mean * cs)
       auto load32 = [&](int ch, float* x, bool fold) {
@@ -346,7 +346,7 @@ k_gemm_tc(GemmTC g, const __grid_constant__ CUtensorMap tmA, const __grid_consta
       };
       if constexpr (EPI == EPI_Q || EPI == EPI_QF32 || EPI == EPI_QKV) {
         // this warp's 64 columns are exactly one head: per-head LayerNorm (q_norm / k_norm) in two passes over TMEM
-        const bool fold = g.st_in != nullptr;
+        const bool fold = g.ln_mr != nullptr;
         int part = 0, cpart = 0;                            // 0 q, 1 k, 2 v (EPI_QKV); q otherwise
         if constexpr (EPI == EPI_QKV) { cpart = c0 / g.Wq; part = cpart + g.part0; }
         const float* nw = part == 1 ? g.kn_w : g.qn_w;
@@ -429,7 +429,7 @@ k_gemm_tc(GemmTC g, const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int ch = 0; ch < 2; ++ch) {
           const int c = c0 + ch * 32;
           float x[32];
-          load32(ch, x, (EPI == EPI_GELU) && g.st_in != nullptr);
+          load32(ch, x, (EPI == EPI_GELU) && g.ln_mr != nullptr);
           if constexpr (EPI == EPI_GELU) {
             if (g.split_out) {
 #pragma unroll
@@ -532,9 +532,35 @@ constexpr size_t GEMM_SMEM = 1024 + GEMM_STAGES * 2 * TILE_BYTES + ST_PER_TILE *
 // ------------------------------------------------------------------------------------------
 // Small HBM-bound stages around the GEMMs
 // ------------------------------------------------------------------------------------------
-// Fourier embedding (attention_blocks.py:112-130) -> T16 with K = 192: [e_hi | e_lo | e_hi]
-__global__ void __launch_bounds__(128) k_embed_tc(QuerySource src, long long n, int F, float pi_mul, uint8_t* __restrict__ T) {
+// Fourier embedding (attention_blocks.py:112-130) -> T16 with K = 192: [e_hi | e_lo | e_hi]; column E (the first padding
+// column) carries the constant 1 that multiplies the bias column of the collapsed c_q . query_proj weight (see QStats).
+// With `qs`: also the ln_1 statistics (mean, rstd) of x0 = query_proj(e) — x0 itself is never formed.  Both are closed forms
+// in e (E = 51 numbers):  mean = e . wbar + bbar,  var = e^T Gc e + 2 e . hc + cc  with the CENTRED second moments of the
+// query_proj rows (no cancellation), evaluated here on the CUDA cores (2.7 kFLOP per point).
+struct QStats { const float* wbar; const float* hc; const float* Gc; const float* scal; int E; };   // wbar[64], hc[64], Gc[64][64], scal = {bbar, cc}
+
+// kF > 0: number of Fourier frequencies known at compile time (8 for every Hunyuan3D-2 checkpoint): the feature vector and
+// the quadratic form are fully unrolled with static indices, so e[] lives in registers and the centred Gram matrix is read
+// from shared memory as broadcast 128-bit loads of its upper triangle (off-diagonals doubled): ~1.4 k FMA per point.
+// kF = 0: generic loops (e[] in local memory), any F.
+template <int kF>
+__global__ void __launch_bounds__(128) k_embed_tc(QuerySource src, long long n, int F, float pi_mul, uint8_t* __restrict__ T,
+                                                  QStats qs, float ln_eps, float2* __restrict__ ln_mr) {
+  constexpr int kE = 3 + 6 * kF, kES = (kE + 3) & ~3;          // static embedding width, Gram row stride (kF > 0)
+  __shared__ __align__(16) float sG[64 * 64 + 2 * 64];
   const int r = threadIdx.x;
+  if (ln_mr) {
+    if constexpr (kF > 0) {
+      for (int t = r; t < kE * kES; t += 128) {
+        const int a = t / kES, bb = t % kES;
+        sG[t] = (bb < a || bb >= kE) ? 0.f : (bb == a ? 1.f : 2.f) * qs.Gc[a * 64 + bb];
+      }
+    } else {
+      for (int t = r; t < qs.E * qs.E; t += 128) sG[t] = qs.Gc[(t / qs.E) * 64 + (t % qs.E)];
+    }
+    for (int t = r; t < 64; t += 128) { sG[64 * 64 + t] = qs.wbar[t]; sG[64 * 64 + 64 + t] = qs.hc[t]; }
+    __syncthreads();
+  }
   const long long qi = (long long)blockIdx.x * TILE_M + r;
   float c[3] = {0.f, 0.f, 0.f};
   long long oi;
@@ -543,13 +569,59 @@ __global__ void __launch_bounds__(128) k_embed_tc(QuerySource src, long long n, 
 #pragma unroll
   for (int i = 0; i < 64; ++i) e[i] = 0.f;
   e[0] = c[0]; e[1] = c[1]; e[2] = c[2];
-  for (int a = 0; a < 3; ++a)
-    for (int f = 0; f < F; ++f) {
-      float s, co;
-      sincosf(__fmul_rn(c[a], exp2f((float)f) * pi_mul), &s, &co);
-      e[3 + a * F + f] = s;
-      e[3 + 3 * F + a * F + f] = co;
+  if constexpr (kF > 0) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int f = 0; f < kF; ++f) {
+        float s, co;
+        sincosf(__fmul_rn(c[a], (float)(1 << f) * pi_mul), &s, &co);
+        e[3 + a * kF + f] = s;
+        e[3 + 3 * kF + a * kF + f] = co;
+      }
+  } else {
+    for (int a = 0; a < 3; ++a)
+      for (int f = 0; f < F; ++f) {
+        float s, co;
+        sincosf(__fmul_rn(c[a], exp2f((float)f) * pi_mul), &s, &co);
+        e[3 + a * F + f] = s;
+        e[3 + 3 * F + a * F + f] = co;
+      }
+  }
+  if (ln_mr) {
+    const float* wb = sG + 64 * 64; const float* hc = wb + 64;
+    float mean = __ldg(qs.scal), lin = 0.f, quad = 0.f;
+    if constexpr (kF > 0) {
+#pragma unroll
+      for (int a = 0; a < kE; ++a) {
+        float t = 0.f;
+#pragma unroll
+        for (int b4 = a & ~3; b4 < kES; b4 += 4) {
+          const float4 u = *reinterpret_cast<const float4*>(sG + a * kES + b4);
+          t = fmaf(u.x, e[b4], t); t = fmaf(u.y, e[b4 + 1], t); t = fmaf(u.z, e[b4 + 2], t); t = fmaf(u.w, e[b4 + 3], t);
+        }
+        quad = fmaf(e[a], t, quad);
+        mean = fmaf(e[a], wb[a], mean);
+        lin = fmaf(e[a], hc[a], lin);
+      }
+    } else {
+      const int E = qs.E;
+      for (int a = 0; a < E; ++a) {
+        const float ea = e[a];
+        float t = 0.f;
+        for (int b = 0; b < E; ++b) t = fmaf(sG[a * E + b], e[b], t);
+        quad = fmaf(ea, t, quad);
+        mean = fmaf(ea, wb[a], mean);
+        lin = fmaf(ea, hc[a], lin);
+      }
     }
+    const float var = fmaxf(quad + 2.f * lin + __ldg(qs.scal + 1), 0.f);
+    ln_mr[qi] = make_float2(mean, rsqrtf(var + ln_eps));          // rows past n: statistics of the zero point, never used
+  }
+  {
+    const int ec = kF > 0 ? kE : 3 + 6 * F;
+    if (ec < 64) e[ec] = 1.0f;                                      // constant column (bias of the collapsed weight)
+  }
   uint8_t* t0 = T + (size_t)blockIdx.x * 3 * TILE_BYTES;
 #pragma unroll
   for (int c16 = 0; c16 < 8; ++c16) {
@@ -678,6 +750,50 @@ __global__ void k_fold_ln(const float* __restrict__ Wsrc, const float* __restric
   }
   for (int o = 16; o; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
   if (lane == 0) { cs[jd] = a; bb[jd] = b + (bias ? bias[j] : 0.f); }
+}
+
+// c_q . query_proj collapsed (both are linear, ln_1 between them only scales / shifts rows):
+//   c_q(ln_1(x0)) = rstd (x0 W'^T - mean cs) + bb   (the LayerNorm fold)   and   x0 = e Wqp^T + bqp
+//   =>  x0 W'^T = e (W' Wqp)^T + W' bqp =: e Wc^T + d        — a K = 51 contraction instead of K = 1024, x0 never formed.
+// Wc_out[j][c] = sum_k Wf[j][k] Wqp[k][c] (c < E),  Wc_out[j][E] = d[j] = sum_k Wf[j][k] bqp[k]   (float64 accumulation)
+__global__ void k_combine_q(const float* __restrict__ Wf, const float* __restrict__ Wqp, const float* __restrict__ bqp, int W, int E,
+                            float* __restrict__ Wc) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= W * (E + 1)) return;
+  const int j = t / (E + 1), c = t % (E + 1);
+  double acc = 0.0;
+  for (int k = 0; k < W; ++k) acc += (double)Wf[(size_t)j * W + k] * (double)(c < E ? Wqp[(size_t)k * E + c] : bqp[k]);
+  Wc[t] = (float)acc;
+}
+// centred moments of the query_proj rows for the closed-form ln_1 statistics of x0 (k_embed_tc): one block
+__global__ void __launch_bounds__(256) k_qstats_consts(const float* __restrict__ Wqp, const float* __restrict__ bqp, int W, int E,
+                                                        float* __restrict__ wbar, float* __restrict__ hc, float* __restrict__ Gc,
+                                                        float* __restrict__ scal) {
+  __shared__ double sw[64];
+  __shared__ double sb;
+  for (int a = threadIdx.x; a < 64; a += 256) {
+    double m = 0.0;
+    if (a < E) { for (int c = 0; c < W; ++c) m += Wqp[(size_t)c * E + a]; m /= W; }
+    sw[a] = m; wbar[a] = (float)m;
+  }
+  if (threadIdx.x == 0) { double m = 0.0; for (int c = 0; c < W; ++c) m += bqp[c]; sb = m / W; }
+  __syncthreads();
+  for (int t = threadIdx.x; t < 64 * 64; t += 256) {
+    const int a = t / 64, b = t % 64;
+    double g = 0.0;
+    if (a < E && b < E) { for (int c = 0; c < W; ++c) g += ((double)Wqp[(size_t)c * E + a] - sw[a]) * ((double)Wqp[(size_t)c * E + b] - sw[b]); g /= W; }
+    Gc[t] = (float)g;
+  }
+  for (int a = threadIdx.x; a < 64; a += 256) {
+    double h = 0.0;
+    if (a < E) { for (int c = 0; c < W; ++c) h += ((double)Wqp[(size_t)c * E + a] - sw[a]) * ((double)bqp[c] - sb); h /= W; }
+    hc[a] = (float)h;
+  }
+  if (threadIdx.x == 0) {
+    double v = 0.0;
+    for (int c = 0; c < W; ++c) v += ((double)bqp[c] - sb) * ((double)bqp[c] - sb);
+    scal[0] = (float)sb; scal[1] = (float)(v / W);
+  }
 }
 
 // ---- operand image builders ----------------------------------------------------------------
@@ -939,7 +1055,8 @@ int hy3d_tc_prepare_weights(hy3d_ctx* ctx) {
   const size_t n_qp = W * 192, n_cq = W * W, n_cp = W * W, n_fc = R * W * W, n_mp = R * W * W, n_cq3 = 3 * W * W;
   const size_t n_ckv3 = 2 * W * 3 * W, n_lp3 = w.has_latents_proj ? W * 3 * (size_t)w.LW : 0;
   const size_t n_cpx = W * (W + 192);                               // [c_proj | query_proj split] concatenated along K
-  HY3D_CUDA(ctx, w.tc.reserve((n_qp + n_cq + n_cp + n_fc + n_mp + n_cq3 + n_ckv3 + n_lp3 + n_cpx) * 2));
+  const size_t n_cqx = W * 192;                                     // c_q . query_proj collapsed: [Wc_hi | Wc_hi | Wc_lo]
+  HY3D_CUDA(ctx, w.tc.reserve((n_qp + n_cq + n_cp + n_fc + n_mp + n_cq3 + n_ckv3 + n_lp3 + n_cpx + n_cqx) * 2));
   __half* base = w.tc.as<__half>();
   __half* p_qp = base; __half* p_cq = p_qp + n_qp; __half* p_cp = p_cq + n_cq; __half* p_fc = p_cp + n_cp; __half* p_mp = p_fc + n_fc;
   auto build = [&](const float* src, int N, int K, int ldw, int mode, __half* dst) -> int {
@@ -949,7 +1066,8 @@ int hy3d_tc_prepare_weights(hy3d_ctx* ctx) {
     return 0;
   };
   // ln_1 folded into c_q, ln_3 into c_fc, ln_post into the head (see GemmTC)
-  HY3D_CUDA(ctx, w.fold.reserve((W + W + R * W + R * W + W + 64 + 4 * W + W) * sizeof(float)));
+  const size_t n_qs = 64 + 64 + 64 * 64 + 64 + W * 64 + W;          // wbar, hc, Gc, scalars, Wc rows (E + 1 <= 64 columns), exact cs
+  HY3D_CUDA(ctx, w.fold.reserve((W + W + R * W + R * W + W + 64 + 4 * W + W + n_qs) * sizeof(float)));
   HY3D_CUDA(ctx, ctx->ws[10].reserve(R * W * W * sizeof(float)));
   float* fb = w.fold.as<float>();
   float* cs_q = fb; float* bb_q = cs_q + W; float* cs_fc = bb_q + W; float* bb_fc = cs_fc + R * W; float* dotw = bb_fc + R * W; float* c12 = dotw + W;
@@ -958,6 +1076,27 @@ int hy3d_tc_prepare_weights(hy3d_ctx* ctx) {
   k_fold_ln<<<(unsigned)((W + 7) / 8), 256, 0, ctx->stream>>>(w.cq_w, w.ln1_w, w.ln1_b, w.cq_b, (int)W, (int)W, Wf, cs_q, bb_q, 0, 0);
   HY3D_LAUNCH_CHECK(ctx);
   if (int rc = build(Wf, (int)W, (int)W, (int)W, 0, p_cq)) return rc;
+  {   // collapsed c_q . query_proj (Wf still holds the gamma-folded c_q weight) + the closed-form ln_1 statistics of x0
+    float* qsb = c12 + 64 + 4 * W + W;
+    float* wbar = qsb; float* hcv = wbar + 64; float* Gc = hcv + 64; float* scal = Gc + 64 * 64; float* Wc = scal + 64;
+    float* cs_qx = Wc + W * 64;
+    const int E1 = w.E + 1;
+    if (E1 > 64) return hy3d_fail(ctx, HY3D_ERR_UNSUPPORTED, "Fourier embedding wider than 63 columns");
+    // the collapsed product is fp32-grade (3-term split): its LayerNorm fold needs the EXACT column sums of the folded weight
+    k_fold_ln<<<(unsigned)((W + 7) / 8), 256, 0, ctx->stream>>>(w.cq_w, w.ln1_w, w.ln1_b, w.cq_b, (int)W, (int)W, Wf, cs_qx, bb_q, 0, 1);
+    HY3D_LAUNCH_CHECK(ctx);
+    k_combine_q<<<(unsigned)((W * E1 + 255) / 256), 256, 0, ctx->stream>>>(Wf, w.qp_w, w.qp_b, (int)W, w.E, Wc);
+    HY3D_LAUNCH_CHECK(ctx);
+    k_qstats_consts<<<1, 256, 0, ctx->stream>>>(w.qp_w, w.qp_b, (int)W, w.E, wbar, hcv, Gc, scal);
+    HY3D_LAUNCH_CHECK(ctx);
+    __half* p_cqx = p_mp + n_mp + n_cq3 + n_ckv3 + n_lp3 + n_cpx;
+    const int saveE = w.E;
+    w.E = E1;                                                        // k_build_b16 mode 1 reads w.E valid columns
+    const int rc = build(Wc, (int)W, 192, E1, 1, p_cqx);
+    w.E = saveE;
+    if (rc) return rc;
+    w.t_cqx = p_cqx; w.qs_wbar = wbar; w.qs_hc = hcv; w.qs_Gc = Gc; w.qs_scal = scal; w.cs_qx = cs_qx;
+  }
   if (int rc = build(w.cproj_w, (int)W, (int)W, (int)W, 0, p_cp)) return rc;
   k_fold_ln<<<(unsigned)((R * W + 7) / 8), 256, 0, ctx->stream>>>(w.fc_w, w.ln3_w, w.ln3_b, w.fc_b, (int)(R * W), (int)W, Wf, cs_fc, bb_fc, 0, 0);
   HY3D_LAUNCH_CHECK(ctx);
@@ -1162,22 +1301,38 @@ static int decode_tc_impl(hy3d_ctx* ctx, const QuerySource& src_in, long long n,
     if (src.mode == 0) src.xyz += 3 * p0;
     else if (src.mode == 1) src.first += p0;
     else src.index += p0;
-    HY3D_PROF(ctx, FAM_EMBED);
-    k_embed_tc<<<Pb, 128, 0, ctx->stream>>>(src, P, w.F, pi_mul, te);
-    HY3D_LAUNCH_CHECK(ctx);
     GemmTC g{};
-    // x0 = query_proj(e): raw fp16 copy + row statistics for the folded ln_1 (+ the fp32 residual when not fused)
-    g.Mb = Pb; g.A = te; g.B = reinterpret_cast<const uint8_t*>(w.t_qp); g.KB = 3; g.N = W; g.Nb = W / BN; g.bias = w.qp_b;
-    g.Rout = fuse_x0 ? nullptr : x; g.Tcopy = tq; g.st_out = st1; g.st_k = 2;
-    if (int rc = launch_gemm<EPI_X0>(ctx, g, FAM_GEMM_QPROJ)) return rc;
-    if (int rc = hy3d_debug_keep(ctx, 0, x, (size_t)Pp * W * 4, 1, Pp, W)) return rc;
-    if (int rc = hy3d_debug_keep(ctx, 1, tq, (size_t)Pp * W * 2, 2, Pp, W)) return rc;
-    // q = q_norm(c_q(ln_1 x0)) * scale * log2e      (ln_1 folded: raw x0 operand, statistics applied in the epilogue)
-    g = GemmTC{}; g.Mb = Pb;
-    g.A = tq; g.B = reinterpret_cast<const uint8_t*>(w.t_cq); g.KB = W / 64; g.N = W; g.Nb = W / BN; g.bias = w.bb_q; g.Tout = ta;
-    g.st_in = st1; g.st_slots = S; g.st_np = ST_COLS; g.cs = w.cs_q; g.ln_eps = 1e-6f;
-    g.qn_w = w.qn_w; g.qn_b = w.qn_b; g.qk_norm = w.qk_norm ? 1 : 0; g.qscale = rsqrtf((float)w.D) * LOG2E;
-    if (int rc = launch_gemm<EPI_Q>(ctx, g, FAM_GEMM_CQ)) return rc;
+    if (fuse_x0) {
+      // q = q_norm(c_q(ln_1(query_proj(e)))) * scale * log2e as ONE K = 192 GEMM: c_q . query_proj collapsed into Wc (the
+      // LayerNorm between them only scales and shifts rows; its statistics are closed forms in e, computed by the embed
+      // kernel).  x0 is never formed, q is fp32-grade (x0 used to be rounded to fp16 on its way into c_q).
+      HY3D_CUDA(ctx, ctx->ln_mr.reserve((size_t)chmax * sizeof(float2)));
+      QStats qs{w.qs_wbar, w.qs_hc, w.qs_Gc, w.qs_scal, w.E};
+      HY3D_PROF(ctx, FAM_EMBED);
+      if (w.F == 8) k_embed_tc<8><<<Pb, 128, 0, ctx->stream>>>(src, P, w.F, pi_mul, te, qs, 1e-6f, ctx->ln_mr.as<float2>());
+      else k_embed_tc<0><<<Pb, 128, 0, ctx->stream>>>(src, P, w.F, pi_mul, te, qs, 1e-6f, ctx->ln_mr.as<float2>());
+      HY3D_LAUNCH_CHECK(ctx);
+      g.Mb = Pb; g.A = te; g.B = reinterpret_cast<const uint8_t*>(w.t_cqx); g.KB = 3; g.N = W; g.Nb = W / BN; g.bias = w.bb_q; g.Tout = ta;
+      g.ln_mr = ctx->ln_mr.as<float2>(); g.cs = w.cs_qx; g.ln_eps = 1e-6f;
+      g.qn_w = w.qn_w; g.qn_b = w.qn_b; g.qk_norm = w.qk_norm ? 1 : 0; g.qscale = rsqrtf((float)w.D) * LOG2E;
+      if (int rc = launch_gemm<EPI_Q>(ctx, g, FAM_GEMM_CQ)) return rc;
+    } else {
+      HY3D_PROF(ctx, FAM_EMBED);
+      k_embed_tc<0><<<Pb, 128, 0, ctx->stream>>>(src, P, w.F, pi_mul, te, QStats{}, 0.f, nullptr);
+      HY3D_LAUNCH_CHECK(ctx);
+      // (diagnostics: activations retained per stage) x0 = query_proj(e): fp32 residual, raw fp16 copy, row statistics
+      g.Mb = Pb; g.A = te; g.B = reinterpret_cast<const uint8_t*>(w.t_qp); g.KB = 3; g.N = W; g.Nb = W / BN; g.bias = w.qp_b;
+      g.Rout = x; g.Tcopy = tq; g.st_out = st1; g.st_k = 2;
+      if (int rc = launch_gemm<EPI_X0>(ctx, g, FAM_GEMM_QPROJ)) return rc;
+      if (int rc = hy3d_debug_keep(ctx, 0, x, (size_t)Pp * W * 4, 1, Pp, W)) return rc;
+      if (int rc = hy3d_debug_keep(ctx, 1, tq, (size_t)Pp * W * 2, 2, Pp, W)) return rc;
+      // q = q_norm(c_q(ln_1 x0)) * scale * log2e      (ln_1 folded: raw x0 operand, statistics applied in the epilogue)
+      g = GemmTC{}; g.Mb = Pb;
+      g.A = tq; g.B = reinterpret_cast<const uint8_t*>(w.t_cq); g.KB = W / 64; g.N = W; g.Nb = W / BN; g.bias = w.bb_q; g.Tout = ta;
+      g.st_in = st1; g.st_slots = S; g.st_np = ST_COLS; g.cs = w.cs_q; g.ln_eps = 1e-6f;
+      g.qn_w = w.qn_w; g.qn_b = w.qn_b; g.qk_norm = w.qk_norm ? 1 : 0; g.qscale = rsqrtf((float)w.D) * LOG2E;
+      if (int rc = launch_gemm<EPI_Q>(ctx, g, FAM_GEMM_CQ)) return rc;
+    }
     if (int rc = hy3d_debug_keep(ctx, 2, ta, (size_t)Pp * W * 2, 2, Pp, W)) return rc;
     {
       AttnTC a{};
@@ -1253,7 +1408,7 @@ int hy3d_tc_sample_q(hy3d_ctx* ctx, const QuerySource& src_in, long long n, floa
     else if (src.mode == 1) src.first += p0;
     else src.index += p0;
     HY3D_PROF(ctx, FAM_SELECT);
-    k_embed_tc<<<Pb, 128, 0, ctx->stream>>>(src, P, w.F, pi_mul, ta);
+    k_embed_tc<0><<<Pb, 128, 0, ctx->stream>>>(src, P, w.F, pi_mul, ta, QStats{}, 0.f, nullptr);
     HY3D_LAUNCH_CHECK(ctx);
     GemmTC g{};
     g.Mb = Pb; g.A = ta; g.B = reinterpret_cast<const uint8_t*>(w.t_qp); g.KB = 3; g.N = W; g.Nb = W / BN; g.bias = w.qp_b; g.Rout = x;
