@@ -953,6 +953,7 @@ int launch_attn(hy3d_ctx* ctx, AttnTC a, bool fast, int fam, bool shifted = fals
   HY3D_PROF(ctx, fam);
   // one K/V set for all query tiles (no per-tile KV groups): pairs of query tiles share every K/V tile they stream
   a.share_kv = (a.tile_group == nullptr && !(ctx->xbits & 0x100)) ? 1 : 0;
+  a.no_pipe = (ctx->xbits & 0x200) ? 1 : 0;
   int rc = 0;
   if (fast) {
     if (ctx->xbits & 0x40) {
