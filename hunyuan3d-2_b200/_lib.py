@@ -85,6 +85,10 @@ SYMBOLS = {
                                     c_i32p, C.c_int32, C.c_int32, C.c_int32]),
     "hy3d_decode_flash": (C.c_int, [C.c_void_p, c_i32p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.POINTER(Coords),
                                     c_i32p, c_f32p]),
+    "hy3d_flash_layout_bins": (C.c_int, [C.c_void_p, c_i32p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.POINTER(Coords),
+                                         C.c_int32, c_i32p, C.c_int64, c_i32p, c_i32p, C.c_int64, c_i32p, c_i32p]),
+    "hy3d_flash_layout_minigrids": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, c_i32p, C.c_int64, c_i32p, c_i32p,
+                                              C.c_int64, c_i32p]),
     "hy3d_flash_selection": (C.c_int, [C.c_void_p, c_i32p, C.c_int64]),
     "hy3d_flash_group_tokens": (C.c_int, [C.c_void_p, c_i32p, C.c_int32]),
     "hy3d_refine_level": (C.c_int, [C.c_void_p, c_f32p, C.c_int32, C.c_int32, C.c_float, C.c_int32, c_i32p, C.c_int64,
@@ -453,6 +457,36 @@ class GeoContext:
         c, keep = self._coords(cell, bmin, axes)
         self._check(self.lib.hy3d_decode_flash(self.h, _ptr(index), index.numel(), dims[0], dims[1], dims[2], C.byref(c),
                                                _ptr(tile_group), _ptr(grid)), "hy3d_decode_flash")
+
+    def flash_layout_bins(self, index: torch.Tensor, dims, cell, bmin, stride: int, with_counts: bool = False):
+        """Group-ordered, 128-padded layout of a refined level's active queries (6^3 spatial bins, stable):
+        -> (pidx, tile_group, sidx, soff[, counts]), device int32; no host synchronisation."""
+        self.sync_stream()
+        nq = int(index.numel())
+        cap = (nq + 216 * 127 + 127) // 128 * 128
+        scap = (nq // stride + 216 + 127) // 128 * 128
+        i32 = dict(dtype=torch.int32, device=self.device)
+        pidx, tile_group = torch.empty(cap, **i32), torch.empty(cap // 128, **i32)
+        sidx, soff = torch.empty(scap, **i32), torch.empty(217, **i32)
+        counts = torch.empty(216, **i32) if with_counts else None
+        c, keep = self._coords(cell, bmin, None)
+        self._check(self.lib.hy3d_flash_layout_bins(self.h, _ptr(index), nq, dims[0], dims[1], dims[2], C.byref(c), int(stride),
+                                                    _ptr(pidx), cap, _ptr(tile_group), _ptr(sidx), scap, _ptr(soff),
+                                                    _ptr(counts)), "hy3d_flash_layout_bins")
+        return (pidx, tile_group, sidx, soff, counts) if with_counts else (pidx, tile_group, sidx, soff)
+
+    def flash_layout_minigrids(self, N: int, mini_grid_num: int, stride: int):
+        """Level-0 layout: mini_grid_num^3 mini-grids of the [N]^3 grid -> (pidx, tile_group, sidx, soff)."""
+        self.sync_stream()
+        m, s = int(mini_grid_num), N // int(mini_grid_num)
+        G, padc, nsamp = m ** 3, (s ** 3 + 127) // 128 * 128, (s ** 3 + stride - 1) // stride
+        cap, scap = G * padc, (G * nsamp + 127) // 128 * 128
+        i32 = dict(dtype=torch.int32, device=self.device)
+        pidx, tile_group = torch.empty(cap, **i32), torch.empty(cap // 128, **i32)
+        sidx, soff = torch.empty(scap, **i32), torch.empty(G + 1, **i32)
+        self._check(self.lib.hy3d_flash_layout_minigrids(self.h, int(N), m, int(stride), _ptr(pidx), cap, _ptr(tile_group),
+                                                         _ptr(sidx), scap, _ptr(soff)), "hy3d_flash_layout_minigrids")
+        return pidx, tile_group, sidx, soff
 
     def flash_selection(self, count: int) -> torch.Tensor:
         out = torch.empty(count, dtype=torch.int32, device=self.device)

@@ -29,19 +29,26 @@ __global__ void k_group_mean(const float* __restrict__ qs, const int* __restrict
   }
 }
 
-// one block per (group, head): similarities to all M tokens, bitonic sort (descending, lower index
-// first on ties), first T token ids -> sel[g][h][0..T)
+// one block per (group, head): similarities to all M (<= 4096) tokens, then the T largest by radix select on the
+// order-preserving integer image of the keys (4 passes of 8 bits over a shared-memory histogram); ties at the
+// threshold go to the lower token index (torch.topk's set on distinct keys; ties are measure-zero in fp32).
+// Output: the T token ids in ascending order -> sel[g][h][0..T) (the attention is order-independent).
 __global__ void __launch_bounds__(1024) k_sim_topk(const float* __restrict__ qbar, const float* __restrict__ k32, int H, int M, int T,
-                                                    int npow2, int* __restrict__ sel, int* __restrict__ ntok) {
-  extern __shared__ unsigned char sm[];
-  float* key = reinterpret_cast<float*>(sm);
-  int* idx = reinterpret_cast<int*>(sm + (size_t)npow2 * 4);
+                                                    int* __restrict__ sel, int* __restrict__ ntok) {
+  constexpr int PER = 4;                        // tokens per thread, consecutive (M <= 4096)
   __shared__ float qv[64];
+  __shared__ unsigned hist[256];
+  __shared__ unsigned sh_prefix, sh_need;
+  __shared__ int wsum[32];
   const int g = blockIdx.x / H, h = blockIdx.x % H;
   if (threadIdx.x < 64) qv[threadIdx.x] = qbar[(size_t)g * H * 64 + h * 64 + threadIdx.x];
+  if (threadIdx.x == 0) { sh_prefix = 0u; sh_need = (unsigned)T; }
   __syncthreads();
-  for (int t = threadIdx.x; t < npow2; t += blockDim.x) {
-    float s = -INFINITY;
+  unsigned key[PER];
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int t = threadIdx.x * PER + i;
+    key[i] = 0u;                                // below every real key (real keys are >= 0x00800000 after the flip of -inf)
     if (t < M) {
       const float4* kr = reinterpret_cast<const float4*>(k32 + ((size_t)h * M + t) * 64);
       float acc = 0.f;
@@ -51,27 +58,73 @@ __global__ void __launch_bounds__(1024) k_sim_topk(const float* __restrict__ qba
         acc = fmaf(qv[4 * d4], kv.x, acc); acc = fmaf(qv[4 * d4 + 1], kv.y, acc);
         acc = fmaf(qv[4 * d4 + 2], kv.z, acc); acc = fmaf(qv[4 * d4 + 3], kv.w, acc);
       }
-      s = acc;
+      const unsigned u = __float_as_uint(acc);
+      key[i] = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+      if (key[i] == 0u) key[i] = 1u;            // keep 0 for "no token" (only a NaN with all mantissa bits could map there)
     }
-    key[t] = s; idx[t] = t;
   }
-  __syncthreads();
-  for (int k = 2; k <= npow2; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = threadIdx.x; t < npow2; t += blockDim.x) {
-        int p = t ^ j;
-        if (p > t) {
-          const bool desc = (t & k) == 0;
-          const float a = key[t], b = key[p];
-          const int ia = idx[t], ib = idx[p];
-          const bool a_first = (a > b) || (a == b && ia < ib);      // a belongs before b in descending order
-          if (desc ? !a_first : a_first) { key[t] = b; key[p] = a; idx[t] = ib; idx[p] = ia; }
+  // threshold = the T-th largest key: fix 8 bits per pass, from the top
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    if (threadIdx.x < 256) hist[threadIdx.x] = 0u;
+    __syncthreads();
+    const unsigned prefix = sh_prefix;
+    const unsigned himask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+#pragma unroll
+    for (int i = 0; i < PER; ++i)
+      if (key[i] != 0u && (key[i] & himask) == prefix) atomicAdd(&hist[(key[i] >> shift) & 255u], 1u);
+    __syncthreads();
+    if (threadIdx.x < 32) {                     // one warp: walk the 256 buckets from the top until `need` is covered
+      unsigned need = sh_need;
+      unsigned c[8]; unsigned tot = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { c[j] = hist[255 - (threadIdx.x * 8 + j)]; tot += c[j]; }
+      unsigned incl = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if ((int)threadIdx.x >= o) incl += v; }
+      unsigned before = incl - tot;             // keys in buckets above this lane's eight
+      if (before < need && need <= incl) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (before < need && need <= before + c[j]) {
+            sh_prefix = prefix | ((unsigned)(255 - (threadIdx.x * 8 + j)) << shift);
+            sh_need = need - before;            // how many keys of this bucket still belong to the top T
+          }
+          before += c[j];
         }
       }
-      __syncthreads();
     }
+    __syncthreads();
   }
-  for (int t = threadIdx.x; t < T; t += blockDim.x) sel[((size_t)g * H + h) * T + t] = idx[t];
+  const unsigned thr = sh_prefix;
+  const int ties = (int)sh_need;                // keys == thr to take, lowest token ids first
+  // ordered compaction: packed scan of (greater, equal) flags
+  int gt = 0, eq = 0;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) { gt += key[i] > thr; eq += (key[i] == thr); }
+  int packed = gt | (eq << 16);
+  int incl = packed;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if ((int)(threadIdx.x & 31) >= o) incl += v; }
+  if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = incl;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int v = wsum[threadIdx.x];
+    int s = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, s, o); if ((int)threadIdx.x >= o) s += u; }
+    wsum[threadIdx.x] = s - v;
+  }
+  __syncthreads();
+  const int excl = wsum[threadIdx.x >> 5] + incl - packed;
+  int ngt = excl & 0xffff, neq = excl >> 16;
+  int* out = sel + ((size_t)g * H + h) * T;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const bool is_gt = key[i] > thr, is_eq = key[i] == thr;
+    if (is_gt || (is_eq && neq < ties)) out[ngt + min(neq, ties)] = threadIdx.x * PER + i;
+    ngt += is_gt; neq += is_eq;
+  }
   if (h == 0 && threadIdx.x == 0) ntok[g] = T;
 }
 
@@ -249,9 +302,8 @@ int hy3d_flash_select(hy3d_ctx* ctx, const int32_t* d_sample_index, int64_t n_sa
     HY3D_PROF(ctx, FAM_SELECT);
     k_group_mean<<<G, 256, 0, ctx->stream>>>(ks.qs.as<float>(), d_sample_off, W, ks.qbar.as<float>());
     HY3D_LAUNCH_CHECK(ctx);
-    int npow2 = 1; while (npow2 < M) npow2 <<= 1;
     HY3D_PROF(ctx, FAM_SELECT);
-    k_sim_topk<<<G * H, 1024, (size_t)npow2 * 8, ctx->stream>>>(ks.qbar.as<float>(), k32, H, M, T, npow2, ks.sel.as<int>(), ks.ntok.as<int>());
+    k_sim_topk<<<G * H, 1024, 0, ctx->stream>>>(ks.qbar.as<float>(), k32, H, M, T, ks.sel.as<int>(), ks.ntok.as<int>());
     HY3D_LAUNCH_CHECK(ctx);
     sel_sg = (long long)H * T; sel_sh = T;
   } else {

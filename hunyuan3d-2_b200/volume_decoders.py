@@ -191,33 +191,6 @@ def flash_topk_budget(M: int) -> int:
     return M // 3
 
 
-def _padded_groups(sorted_index: torch.Tensor, counts: torch.Tensor, stride: int, total_cap: int, sample_cap: int):
-    """Lay a group-sorted query list out for the device: every group starts on a 128-query tile
-    boundary (padding = -1), plus the per-tile group id and the sub-sampled queries (every
-    ``stride``-th query of each group, reference ``q[:, :, ::stride]``).  All device-side torch ops,
-    no host synchronisation; ``total_cap`` / ``sample_cap`` are static upper bounds."""
-    dev = sorted_index.device
-    G = counts.numel()
-    pc = (counts + 127) // 128 * 128
-    cum_pc = torch.cumsum(pc, 0)
-    goff = cum_pc - pc                                   # padded start of each group
-    start = torch.cumsum(counts, 0) - counts             # sorted start of each group
-    gid = torch.repeat_interleave(torch.arange(G, device=dev), counts, output_size=sorted_index.numel())
-    pos = torch.arange(sorted_index.numel(), device=dev)
-    within = pos - start[gid]
-    pidx = torch.full((total_cap,), -1, dtype=torch.int32, device=dev)
-    pidx[goff[gid] + within] = sorted_index.to(torch.int32)
-    tiles = torch.arange(total_cap // 128, device=dev) * 128
-    tile_group = torch.bucketize(tiles, cum_pc, right=True).clamp_(max=G - 1).to(torch.int32)
-    ns = (counts + stride - 1) // stride                 # samples per group
-    soff = torch.cumsum(ns, 0) - ns
-    is_s = (within % stride) == 0
-    sidx = torch.full((sample_cap,), -1, dtype=torch.int32, device=dev)
-    sidx[(soff[gid] + within // stride)[is_s]] = sorted_index[is_s].to(torch.int32)
-    sample_off = torch.cat([soff, (soff[-1:] + ns[-1:])]).to(torch.int32)
-    return pidx, tile_group, sidx, sample_off
-
-
 class FlashVDMVolumeDecoding:
     """FlashVDM decoding with adaptive KV selection (reference volume_decoders.py:280-435) ->
     latents.dtype [B,N',N',N'] (N' = 381 for octree 384), NaN = unvisited.
@@ -251,15 +224,8 @@ class FlashVDMVolumeDecoding:
             T = flash_topk_budget(latents.shape[1])
             # ---- level 0: mini_grid_num^3 mini-grids, each with its own top-k tokens (reference :343-371)
             N0 = levels[0] + 1
-            m, s = mini_grid_num, N0 // mini_grid_num
-            lin = torch.arange(N0 ** 3, device=dev, dtype=torch.int64).view(m, s, m, s, m, s)
-            order = lin.permute(0, 2, 4, 1, 3, 5).reshape(m ** 3, s ** 3)
-            G0 = m ** 3
-            counts = torch.full((G0,), s ** 3, dtype=torch.int64, device=dev)
-            padc = (s ** 3 + 127) // 128 * 128
-            nsamp = (s ** 3 + 99) // 100
-            pidx, tile_group, sidx, soff = _padded_groups(order.reshape(-1), counts, 100, G0 * padc,
-                                                          (G0 * nsamp + 127) // 128 * 128)
+            G0 = mini_grid_num ** 3
+            pidx, tile_group, sidx, soff = ctx.flash_layout_minigrids(N0, mini_grid_num, 100)
             axes = axis_tables(bounds, levels[0])
             ctx.flash_select(sidx, (N0, N0, N0), soff, G0, T, False, axes=axes)      # level 0 is 'mean' in both modes
             grid = torch.empty((N0, N0, N0), dtype=torch.float32, device=dev)
@@ -277,20 +243,8 @@ class FlashVDMVolumeDecoding:
                 nq = int(index.numel())
                 queries.append(nq)
                 if nq:
-                    idx64 = index.long()
-                    ijk = torch.stack((idx64 // (n * n), (idx64 // n) % n, idx64 % n), 1)
-                    # reference :394-403, op for op in float32
-                    pts = ijk * torch.tensor(cell, dtype=torch.float32, device=dev) + torch.tensor(bmin32, device=dev)
-                    mn, mx = pts.min(0).values, pts.max(0).values
-                    q = torch.floor((pts - mn) / (mx - mn) * (6 - 0.001)).long()
-                    bins = q[:, 0] * 36 + q[:, 1] * 6 + q[:, 2]
-                    bins = bins.clamp_(0, 215)             # a degenerate axis (max == min) yields NaN -> garbage ids
-                    order = torch.sort(bins, stable=True).indices
-                    counts = torch.bincount(bins, minlength=216)
-                    stride = 30 if merge else 50
-                    cap = (nq + 216 * 127 + 127) // 128 * 128
-                    scap = (nq // stride + 216 + 127) // 128 * 128
-                    pidx, tile_group, sidx, soff = _padded_groups(index[order], counts, stride, cap, scap)
+                    # bin ids (reference :394-403, float32 op for op), stable sort, per-bin padding and samples: one device pass
+                    pidx, tile_group, sidx, soff = ctx.flash_layout_bins(index, (n, n, n), cell, bmin32, 30 if merge else 50)
                     ctx.flash_select(sidx, (n, n, n), soff, 216, T, merge, cell=cell, bmin=bmin32)
                     ctx.decode_flash(pidx, (n, n, n), tile_group, nxt, cell=cell, bmin=bmin32)
                 grid = nxt

@@ -169,6 +169,22 @@ int hy3d_flash_select(hy3d_ctx* ctx, const int32_t* d_sample_index, int64_t n_sa
  * tile's group (d_tile_group: DEVICE int32 [n/128]); logits scattered to d_grid[d_index[q]]. */
 int hy3d_decode_flash(hy3d_ctx* ctx, const int32_t* d_index, int64_t n, int32_t n0, int32_t n1, int32_t n2,
                       const hy3d_coords* coords, const int32_t* d_tile_group, float* d_grid);
+/* Query layout of a refined FlashVDM level, all on the device (no host synchronisation): replaces
+ * volume_decoders.py:394-412 -- bin id of every active query (float32 op for op: floor((p - min) /
+ * (max - min) * (6 - 0.001)) per axis, 6^3 = 216 bins, ids clamped to [0, 215]), STABLE sort by bin,
+ * per-bin slices and the q[:, :, ::stride] sub-sampling.  d_index: the level's ordered active indices
+ * (hy3d_refine_level); coords must be mode 2.  Outputs (DEVICE int32): d_pidx[cap] every bin starting on
+ * a multiple of 128, -1 = padding; d_tile_group[cap/128]; d_sidx[scap] every stride-th query of each bin,
+ * -1 = padding; d_soff[217]; d_counts[216] (optional, may be NULL).  Static capacities:
+ * cap >= round128(n + 216*127), scap >= n/stride + 216. */
+int hy3d_flash_layout_bins(hy3d_ctx* ctx, const int32_t* d_index, int64_t n, int32_t n0, int32_t n1, int32_t n2,
+                           const hy3d_coords* coords, int32_t stride, int32_t* d_pidx, int64_t cap, int32_t* d_tile_group,
+                           int32_t* d_sidx, int64_t scap, int32_t* d_soff, int32_t* d_counts);
+/* The same layout for level 0: mini_grid_num^3 mini-grids of (N/mini_grid_num)^3 voxels each, queries of a
+ * mini-grid in lexicographic order (volume_decoders.py:343-356).  cap = G*round128(s^3),
+ * scap >= G*ceil(s^3/stride), d_soff[G+1]. */
+int hy3d_flash_layout_minigrids(hy3d_ctx* ctx, int32_t N, int32_t mini_grid_num, int32_t stride, int32_t* d_pidx, int64_t cap,
+                                int32_t* d_tile_group, int32_t* d_sidx, int64_t scap, int32_t* d_soff);
 /* Selected token ids / per-group token counts of the last hy3d_flash_select (parity tests). */
 int hy3d_flash_selection(hy3d_ctx* ctx, int32_t* d_out, int64_t count);
 int hy3d_flash_group_tokens(hy3d_ctx* ctx, int32_t* d_out, int32_t G);

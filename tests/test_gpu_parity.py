@@ -414,6 +414,81 @@ def test_flashvdm_level0_selection_and_logits(dev, ctx):
         assert d < (LOGIT_TOL if g not in bad_groups else 2e-2), (g, d)
 
 
+def _layout_reference(index, n, cell, bmin, stride):
+    """Host restatement of reference vd:394-412 for the padded layout: oracle bin ids, stable sort, 128-padding, samples."""
+    idx = np.stack(np.unravel_index(index.astype(np.int64), (n, n, n)), 1)
+    pts = (idx.astype(np.float32) * cell.astype(np.float32) + bmin.astype(np.float32)).astype(np.float32)
+    with np.errstate(all="ignore"):
+        bins = OV.flash_bins(pts)
+    bins = np.clip(bins, 0, 215)
+    order = np.argsort(bins, kind="stable")
+    counts = np.bincount(bins, minlength=216)
+    cap = (len(index) + 216 * 127 + 127) // 128 * 128
+    pidx = np.full(cap, -1, np.int32)
+    tile_group = np.full(cap // 128, 215, np.int32)
+    samples, soff, pos, at = [], [0], 0, 0
+    for g in range(216):
+        members = index[order[at:at + counts[g]]]
+        at += counts[g]
+        pc = (counts[g] + 127) // 128 * 128
+        pidx[pos:pos + counts[g]] = members
+        tile_group[pos // 128:(pos + pc) // 128] = g
+        pos += pc
+        samples.append(members[::stride])
+        soff.append(soff[-1] + len(samples[-1]))
+    return pidx, tile_group, np.concatenate(samples).astype(np.int32), np.asarray(soff, np.int32), counts.astype(np.int32)
+
+
+@pytest.mark.parametrize("case", ["shell", "random", "flat_axis", "tiny", "empty"])
+def test_flash_layout_bins_matches_reference_restatement(case, dev, ctx):
+    """hy3d_flash_layout_bins: bin ids, stable order, padding, per-tile group and stride samples, bit for bit."""
+    rng = np.random.default_rng(11)
+    n = 97
+    if case == "shell":
+        g = np.linalg.norm(np.stack(np.meshgrid(*[np.arange(n)] * 3, indexing="ij"), -1) - 48.0, axis=-1)
+        index = np.nonzero((np.abs(g - 30.0) < 2.0).reshape(-1))[0]
+    elif case == "random":
+        index = np.sort(rng.choice(n ** 3, 70001, replace=False))
+    elif case == "flat_axis":                                    # max == min on axis 0: NaN bin component -> clamped ids
+        index = np.sort(rng.choice(n * n, 5000, replace=False)) + 40 * n * n
+    elif case == "tiny":
+        index = np.array([5, 77, 4000, 900000], np.int64)
+    else:
+        index = np.zeros(0, np.int64)
+    index = index.astype(np.int32)
+    cell = (np.full(3, 2.02) / (n - 1)).astype(np.float32)
+    bmin = np.full(3, -1.01, np.float32)
+    for stride in (50, 30):
+        pidx, tg, sidx, soff, counts = ctx.flash_layout_bins(torch.from_numpy(index).to(dev), (n, n, n), cell, bmin, stride, with_counts=True)
+        if len(index):
+            rp, rt, rs, ro, rc = _layout_reference(index, n, cell, bmin, stride)
+        else:
+            rp, rt = np.full(pidx.numel(), -1, np.int32), np.full(tg.numel(), 215, np.int32)
+            rs, ro, rc = np.zeros(0, np.int32), np.zeros(217, np.int32), np.zeros(216, np.int32)
+        assert np.array_equal(counts.cpu().numpy(), rc)
+        assert np.array_equal(soff.cpu().numpy(), ro)
+        assert np.array_equal(pidx.cpu().numpy(), rp)
+        s = sidx.cpu().numpy()
+        assert np.array_equal(s[:len(rs)], rs) and bool((s[len(rs):] == -1).all())
+        # tiles past the last bin hold only padding; the reference restatement leaves them at G-1 too
+        assert np.array_equal(tg.cpu().numpy(), rt)
+
+
+def test_flash_layout_minigrids_matches_oracle_order(dev, ctx):
+    N, m, stride = 32, 4, 100
+    pidx, tg, sidx, soff = ctx.flash_layout_minigrids(N, m, stride)
+    order = OV.flash_minigrid_order(N, m)                         # [64, 512]
+    G, s3 = order.shape
+    padc = (s3 + 127) // 128 * 128
+    p = pidx.cpu().numpy().reshape(G, padc)
+    assert np.array_equal(p[:, :s3], order.astype(np.int32)) and bool((p[:, s3:] == -1).all())
+    assert np.array_equal(tg.cpu().numpy(), np.repeat(np.arange(G, dtype=np.int32), padc // 128))
+    ns = (s3 + stride - 1) // stride
+    assert np.array_equal(soff.cpu().numpy(), np.arange(G + 1, dtype=np.int32) * ns)
+    sv = sidx.cpu().numpy()
+    assert np.array_equal(sv[:G * ns].reshape(G, ns), order[:, ::stride].astype(np.int32)) and bool((sv[G * ns:] == -1).all())
+
+
 # ------------------------------------------------------------------ round 2: BASELINE configurations (goldens *_r2)
 def test_refine_odd_levels_matches_oracle(ctx):
     """Fine grids of 2n voxels per axis (the coarse level is an odd r // 2, reference vd:202-208): indices are laid out on the
