@@ -88,6 +88,7 @@ constexpr size_t ATT_SMEM = 1024 + ATT_TILES_BYTES + 512 + 2048;       // + barr
 __device__ __forceinline__ uint32_t attn_setup(uint8_t* smem, AttnBars& B, int softmax_warps, int share_kv) {
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATT_TILES_BYTES);
   B.b0 = smem_u32(bars);
+  asm volatile("" : "+r"(B.b0));        // opaque: otherwise every barrier use re-derives the shared-window address from special registers
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * AttnBars::NB);
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
@@ -130,7 +131,8 @@ __device__ __forceinline__ AttnItem attn_item(const AttnTC& g, int item, int a) 
 // Producer warp of stream a (whole warp converged).  share_kv: called once (a = 0) and feeds both streams.
 __device__ __forceinline__ void attn_producer(const AttnTC& g, const AttnBars& B, uint8_t* smem, int a) {
   const bool sh = g.share_kv != 0;
-  uint8_t* ring = smem + 2 * TILE_BYTES + (sh ? 0 : a * ATT_SLOTS * TILE_BYTES);
+  uint32_t ring32 = smem_u32(smem + 2 * TILE_BYTES + (sh ? 0 : a * ATT_SLOTS * TILE_BYTES)), q32 = smem_u32(smem);
+  asm volatile("" : "+r"(ring32), "+r"(q32));
   const int nslots = sh ? 2 * ATT_SLOTS : ATT_SLOTS;
   const int nitems = attn_num_items(g), nkv = g.nkv;
   int s = 0; uint32_t ph = 0, qph = 0;
@@ -139,7 +141,7 @@ __device__ __forceinline__ void attn_producer(const AttnTC& g, const AttnBars& B
     mbar_wait(empty, ph ^ 1);
     if (elect_one()) {
       mbar_arrive_expect_tx(full, TILE_BYTES);
-      bulk_g2s(smem_u32(ring + s * TILE_BYTES), src, TILE_BYTES, full);
+      bulk_g2s(ring32 + s * TILE_BYTES, src, TILE_BYTES, full);
     }
     __syncwarp();
     if (++s == nslots) { s = 0; ph ^= 1; }
@@ -151,7 +153,7 @@ __device__ __forceinline__ void attn_producer(const AttnTC& g, const AttnBars& B
       mbar_wait(B.qempty(aa), qph ^ 1);
       if (elect_one()) {
         mbar_arrive_expect_tx(B.qfull(aa), TILE_BYTES);
-        bulk_g2s(smem_u32(smem + aa * TILE_BYTES), g.Q + ((size_t)iq.qt * g.H + iq.h) * TILE_BYTES, TILE_BYTES, B.qfull(aa));
+        bulk_g2s(q32 + aa * TILE_BYTES, g.Q + ((size_t)iq.qt * g.H + iq.h) * TILE_BYTES, TILE_BYTES, B.qfull(aa));
       }
       __syncwarp();
     }
@@ -175,13 +177,16 @@ __device__ __forceinline__ void attn_producer(const AttnTC& g, const AttnBars& B
 __device__ __forceinline__ void attn_mma(const AttnTC& g, const AttnBars& B, uint8_t* smem, uint32_t tmem, int a) {
   const bool sh = g.share_kv != 0;
   uint8_t* sQ = smem + a * TILE_BYTES;
-  uint8_t* ring = smem + 2 * TILE_BYTES + (sh ? 0 : a * ATT_SLOTS * TILE_BYTES);
   const int nslots = sh ? 2 * ATT_SLOTS : ATT_SLOTS;
   const int nitems = attn_num_items(g), nkv = g.nkv;
   const uint32_t idesc_s = make_idesc_f16(128, 128);
   const uint32_t idesc_o = make_idesc_f16(128, 64);
-  const uint32_t d_s = tmem + TM_S0 + a * 128, d_o = tmem + TM_O0 + a * 64, a_p = tmem + TM_P0 + a * 64;
-  const uint64_t qd = make_desc_sw128(smem_u32(sQ));
+  uint32_t d_s = tmem + TM_S0 + a * 128, d_o = tmem + TM_O0 + a * 64, a_p = tmem + TM_P0 + a * 64;
+  uint64_t qd = make_desc_sw128(smem_u32(sQ));
+  // descriptor of ring slot 0; slot s adds s * TILE_BYTES / 16 to the address field.  Opaque (see attn_setup): this warp's
+  // wake-up -> MMA issue path is on the serial chain of the stream.
+  uint64_t ring_d = make_desc_sw128(smem_u32(smem + 2 * TILE_BYTES + (sh ? 0 : a * ATT_SLOTS * TILE_BYTES)));
+  asm volatile("" : "+r"(d_s), "+r"(d_o), "+r"(a_p), "+l"(qd), "+l"(ring_d));
   int s = 0; uint32_t ph = 0, qph = 0, sph = 0, pph = 0;
   // instrumented launches (hy3d_debug_timers): cycles this warp waits for 0 K tile, 1 S buffer free, 2 V tile, 3 P stored
   const bool tmr = g.timers != nullptr && blockIdx.x == 0;
@@ -195,7 +200,7 @@ __device__ __forceinline__ void attn_mma(const AttnTC& g, const AttnBars& B, uin
     mbar_wait(B.sempty(a), sph ^ 1); sph ^= 1;
     tick(1);
     fence_after_sync();
-    const uint64_t bd = make_desc_sw128(smem_u32(ring + s * TILE_BYTES));
+    const uint64_t bd = ring_d + (uint64_t)(s * (TILE_BYTES / 16));
     if (elect_one()) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) mma_f16_ss(d_s, qd + 2 * k, bd + 2 * k, idesc_s, k != 0);
@@ -213,7 +218,7 @@ __device__ __forceinline__ void attn_mma(const AttnTC& g, const AttnBars& B, uin
     mbar_wait(B.pfull(a), pph); pph ^= 1;
     tick(3);
     fence_after_sync();
-    const uint64_t bd = make_desc_sw128(smem_u32(ring + s * TILE_BYTES));
+    const uint64_t bd = ring_d + (uint64_t)(s * (TILE_BYTES / 16));
     if (elect_one()) {
 #pragma unroll
       for (int k = 0; k < 8; ++k)                      // 16 tokens (8 TMEM columns of fp16 pairs) per MMA
@@ -294,12 +299,15 @@ __global__ void __launch_bounds__(ATT_FAST_THREADS, 1) k_attn_fast(AttnTC g) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nitems = attn_num_items(g), nkv = g.nkv;
 
-  // (no setmaxnreg here: registers can only be moved inside the CTA's launch allocation, 640 x 96, and the
-  //  softmax threads fit in 96)
+  // Registers move inside the CTA's launch allocation (640 x 96): the role warpgroup gives up 40 per thread, the four
+  // softmax warpgroups take 8 more each (128 x 56 + 512 x 104 <= 640 x 96) — at 96 the softmax loop spilled and the
+  // compiler re-derived every barrier / TMEM address from %tid and the shared window base at each use.
   if (warp < 4) {
+    reg_dealloc<56>();
     if ((warp & 1) == 0) { if (!g.share_kv || warp == 0) attn_producer(g, B, smem, warp >> 1); }   // shared ring: one producer
     else attn_mma(g, B, smem, tmem, warp >> 1);
   } else {
+    reg_alloc<104>();
     const int a = (warp - 4) >> 3;                      // head stream
     const int hh = ((warp - 4) >> 2) & 1;               // column half: tokens [64 hh, 64 hh + 64) of every KV tile
     const int q = warp & 3;                             // TMEM lane quadrant
@@ -308,6 +316,12 @@ __global__ void __launch_bounds__(ATT_FAST_THREADS, 1) k_attn_fast(AttnTC g) {
     const uint32_t t_s = tmem + TM_S0 + a * 128 + hh * 64 + lane_off;
     const uint32_t t_p = tmem + TM_P0 + a * 64 + hh * 32 + lane_off;
     const uint32_t t_o = tmem + TM_O0 + a * 64 + hh * 32 + lane_off;
+    // Opaque copies: left to itself the compiler re-derives the barrier addresses (S2UR %cluster_ctarank / shared-window
+    // base, align, add) and the TMEM addresses (S2R %tid, shifts) at every use inside the tile loop — ~100 of its ~330
+    // instructions per tile, several of them long-latency special-register reads on the stream's serial chain.
+    uint32_t bar_sfull = B.sfull(a), bar_sempty = B.sempty(a), bar_pfull = B.pfull(a), bar_pvdone = B.pvdone(a);
+    uint32_t ts_ = t_s, tp_ = t_p, lane0 = lane == 0;
+    asm volatile("" : "+r"(bar_sfull), "+r"(bar_sempty), "+r"(bar_pfull), "+r"(bar_pvdone), "+r"(ts_), "+r"(tp_), "+r"(lane0));
     uint32_t sfull_ph = 0, pv_ph = 0;
     long long tk0 = 0, tk[6] = {0, 0, 0, 0, 0, 0};
 #define HY3D_TICK(i) if constexpr (kTimers) { const long long t_ = clock64(); tk[i] += t_ - tk0; tk0 = t_; }
@@ -325,16 +339,16 @@ __global__ void __launch_bounds__(ATT_FAST_THREADS, 1) k_attn_fast(AttnTC g) {
       // exponentials — the probes travel in the shadow of that work — and the blocking waits run only if a probe failed.
       bool s_ready = false;                              // S(j) already known complete
       for (int j = 0; j < nkv; ++j) {
-        if (!s_ready) mbar_wait(B.sfull(a), sfull_ph);
+        if (!s_ready) mbar_wait(bar_sfull, sfull_ph);
         sfull_ph ^= 1;
         fence_after_sync();
         HY3D_TICK(0)
         // software pipeline over the two 32-column halves of this thread's 64 scores: the second tcgen05.ld is in flight
         // while the first half's exponentials run (one TMEM round trip per tile off the stream's serial chain)
         uint32_t sv[64];
-        HY3D_TMEM_LD32(t_s, sv);
-        if (g.no_pipe) { HY3D_TMEM_LD32(t_s + 32, (sv + 32)); tmem_wait_ld(); }      // (experiment bit 0x200: both halves up front)
-        else { tmem_wait_ld(); HY3D_TMEM_LD32(t_s + 32, (sv + 32)); }
+        HY3D_TMEM_LD32(ts_, sv);
+        if (g.no_pipe) { HY3D_TMEM_LD32(ts_ + 32, (sv + 32)); tmem_wait_ld(); }      // (experiment bit 0x200: both halves up front)
+        else { tmem_wait_ld(); HY3D_TMEM_LD32(ts_ + 32, (sv + 32)); }
         HY3D_TICK(1)
         const int valid = ntok - j * 128 - hh * 64;    // columns >= valid are padding tokens (last tile of a ragged count)
         bool pv_ok = j == 0, s_ok = false;
@@ -351,8 +365,8 @@ __global__ void __launch_bounds__(ATT_FAST_THREADS, 1) k_attn_fast(AttnTC g) {
 #pragma unroll
             for (int i = i0; i < i1; ++i) {
               if (i == 24) {                           // probes: PV(j-1) consumed the previous P?  S(j+1) computed?
-                if (j > 0) pv_ok = mbar_test_wait(B.pvdone(a), pv_ph);
-                if (j + 1 < nkv) s_ok = mbar_test_wait(B.sfull(a), sfull_ph);
+                if (j > 0) pv_ok = mbar_test_wait(bar_pvdone, pv_ph);
+                if (j + 1 < nkv) s_ok = mbar_test_wait(bar_sfull, sfull_ph);
               }
               const float x0 = __uint_as_float(sv[2 * i]), x1 = __uint_as_float(sv[2 * i + 1]);
               float p0, p1;
@@ -375,7 +389,7 @@ __global__ void __launch_bounds__(ATT_FAST_THREADS, 1) k_attn_fast(AttnTC g) {
         HY3D_TMEM_WAIT_LD32((sv + 32));                // second half has landed (tied to its registers)
         fence_before_sync();
         __syncwarp();
-        if (lane == 0) mbar_arrive(B.sempty(a));       // S is in registers: the next S MMA may overwrite it
+        if (lane0) mbar_arrive(bar_sempty);       // S is in registers: the next S MMA may overwrite it
         if (cshift != 0.f) {
 #pragma unroll
           for (int i = 16; i < 32; ++i) {
@@ -386,14 +400,14 @@ __global__ void __launch_bounds__(ATT_FAST_THREADS, 1) k_attn_fast(AttnTC g) {
         }
         exp_pairs(16, 32);
         HY3D_TICK(2)
-        if (j > 0) { if (!pv_ok) mbar_wait(B.pvdone(a), pv_ph); pv_ph ^= 1; }   // PV(j-1) has consumed the previous P
+        if (j > 0) { if (!pv_ok) mbar_wait(bar_pvdone, pv_ph); pv_ph ^= 1; }   // PV(j-1) has consumed the previous P
         s_ready = s_ok;
         HY3D_TICK(3)
-        HY3D_TMEM_ST32(t_p, sv);
+        HY3D_TMEM_ST32(tp_, sv);
         tmem_wait_st();
         fence_before_sync();
         __syncwarp();
-        if (lane == 0) mbar_arrive(B.pfull(a));
+        if (lane0) mbar_arrive(bar_pfull);
         HY3D_TICK(4)
       }
       // ---- finalize: row sums of the two column halves through shared memory, O / l -> fp16 tile (q-tile, head) ----
@@ -409,7 +423,7 @@ __global__ void __launch_bounds__(ATT_FAST_THREADS, 1) k_attn_fast(AttnTC g) {
         const int e = qt * (g.H >> 1) + (h >> 1);
         if (atomicExch(&g.redo_flag[e], 1) == 0) g.redo_list[atomicAdd(g.redo_count, 1)] = e;
       }
-      mbar_wait(B.pvdone(a), pv_ph); pv_ph ^= 1;
+      mbar_wait(bar_pvdone, pv_ph); pv_ph ^= 1;
       fence_after_sync();
       uint8_t* tile = g.O + ((size_t)qt * (g.split_out ? 3 : 1) * g.H + h) * TILE_BYTES;
       {
