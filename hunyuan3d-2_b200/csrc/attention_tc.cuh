@@ -321,7 +321,8 @@ __global__ void __launch_bounds__(ATT_FAST_THREADS, 1) k_attn_fast(AttnTC g) {
     // instructions per tile, several of them long-latency special-register reads on the stream's serial chain.
     uint32_t bar_sfull = B.sfull(a), bar_sempty = B.sempty(a), bar_pfull = B.pfull(a), bar_pvdone = B.pvdone(a);
     uint32_t ts_ = t_s, tp_ = t_p, lane0 = lane == 0;
-    asm volatile("" : "+r"(bar_sfull), "+r"(bar_sempty), "+r"(bar_pfull), "+r"(bar_pvdone), "+r"(ts_), "+r"(tp_), "+r"(lane0));
+    int col0 = hh * 64;                                  // first token column of this thread inside a KV tile
+    asm volatile("" : "+r"(bar_sfull), "+r"(bar_sempty), "+r"(bar_pfull), "+r"(bar_pvdone), "+r"(ts_), "+r"(tp_), "+r"(lane0), "+r"(col0));
     uint32_t sfull_ph = 0, pv_ph = 0;
     long long tk0 = 0, tk[6] = {0, 0, 0, 0, 0, 0};
 #define HY3D_TICK(i) if constexpr (kTimers) { const long long t_ = clock64(); tk[i] += t_ - tk0; tk0 = t_; }
@@ -350,7 +351,7 @@ __global__ void __launch_bounds__(ATT_FAST_THREADS, 1) k_attn_fast(AttnTC g) {
         if (g.no_pipe) { HY3D_TMEM_LD32(ts_ + 32, (sv + 32)); tmem_wait_ld(); }      // (experiment bit 0x200: both halves up front)
         else { tmem_wait_ld(); HY3D_TMEM_LD32(ts_ + 32, (sv + 32)); }
         HY3D_TICK(1)
-        const int valid = ntok - j * 128 - hh * 64;    // columns >= valid are padding tokens (last tile of a ragged count)
+        const int valid = ntok - j * 128 - col0;     // columns >= valid are padding tokens (last tile of a ragged count)
         bool pv_ok = j == 0, s_ok = false;
         if (cshift != 0.f) {                           // (warp-uniform) s - c_h: one FADD2 per pair, only for heads that need it
 #pragma unroll
@@ -487,6 +488,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) k_attn_tc(AttnTC g) {
     const uint32_t t_s = tmem + TM_S0 + a * 128 + ((uint32_t)(q * 32) << 16);
     const uint32_t t_o = tmem + TM_O0 + a * 64 + ((uint32_t)(q * 32) << 16);
     const uint32_t t_p = tmem + TM_P0 + a * 64 + ((uint32_t)(q * 32) << 16);
+    uint32_t bar_sfull = B.sfull(a), bar_sempty = B.sempty(a), bar_pfull = B.pfull(a), bar_pvdone = B.pvdone(a);
+    uint32_t ts_ = t_s, tp_ = t_p, to_ = t_o, lane0 = lane == 0;       // opaque copies, see k_attn_fast
+    asm volatile("" : "+r"(bar_sfull), "+r"(bar_sempty), "+r"(bar_pfull), "+r"(bar_pvdone), "+r"(ts_), "+r"(tp_), "+r"(to_), "+r"(lane0));
     uint32_t sfull_ph = 0, pv_ph = 0;
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
       const AttnItem wi = attn_item(g, item, a);
@@ -494,15 +498,15 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) k_attn_tc(AttnTC g) {
       const int ntok = g.group_ntok ? g.group_ntok[g.tile_group ? g.tile_group[qt] : 0] : g.ntok;
       float m = -INFINITY, l = 0.f;
       for (int j = 0; j < nkv; ++j) {
-        mbar_wait(B.sfull(a), sfull_ph); sfull_ph ^= 1;
+        mbar_wait(bar_sfull, sfull_ph); sfull_ph ^= 1;
         fence_after_sync();
         uint32_t sv[128];
-        HY3D_TMEM_LD32(t_s, sv); HY3D_TMEM_LD32(t_s + 32, (sv + 32));
-        HY3D_TMEM_LD32(t_s + 64, (sv + 64)); HY3D_TMEM_LD32(t_s + 96, (sv + 96));
+        HY3D_TMEM_LD32(ts_, sv); HY3D_TMEM_LD32(ts_ + 32, (sv + 32));
+        HY3D_TMEM_LD32(ts_ + 64, (sv + 64)); HY3D_TMEM_LD32(ts_ + 96, (sv + 96));
         tmem_wait_ld();
         fence_before_sync();
         __syncwarp();
-        if (lane == 0) mbar_arrive(B.sempty(a));
+        if (lane0) mbar_arrive(bar_sempty);
         const int valid = ntok - j * 128;              // columns >= valid are padding tokens
         if (valid < 128) {                             // only the last tile of a ragged token count
 #pragma unroll
@@ -526,18 +530,18 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) k_attn_tc(AttnTC g) {
         // probabilities sit packed in registers, so the MMA has the whole exp phase to finish.
         bool waited = (j == 0);
         if (j > 0 && __any_sync(0xffffffffu, need)) {
-          mbar_wait(B.pvdone(a), pv_ph); pv_ph ^= 1; waited = true;
+          mbar_wait(bar_pvdone, pv_ph); pv_ph ^= 1; waited = true;
           fence_after_sync();
           const float sc = need ? ex2(m - m_new) : 1.f;
           l *= sc;
 #pragma unroll 1
           for (int c = 0; c < 2; ++c) {
             uint32_t ov[32];
-            HY3D_TMEM_LD32(t_o + c * 32, ov);
+            HY3D_TMEM_LD32(to_ + c * 32, ov);
             tmem_wait_ld();
 #pragma unroll
             for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * sc);
-            HY3D_TMEM_ST32(t_o + c * 32, ov);
+            HY3D_TMEM_ST32(to_ + c * 32, ov);
           }
           tmem_wait_st();
         }
@@ -552,22 +556,22 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) k_attn_tc(AttnTC g) {
           sv[i] = pack_h2(p0, p1);
         }
         l += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
-        if (!waited) { mbar_wait(B.pvdone(a), pv_ph); pv_ph ^= 1; }
-        HY3D_TMEM_ST32(t_p, sv); HY3D_TMEM_ST32(t_p + 32, (sv + 32));
+        if (!waited) { mbar_wait(bar_pvdone, pv_ph); pv_ph ^= 1; }
+        HY3D_TMEM_ST32(tp_, sv); HY3D_TMEM_ST32(tp_ + 32, (sv + 32));
         tmem_wait_st();
         fence_before_sync();
         __syncwarp();
-        if (lane == 0) mbar_arrive(B.pfull(a));
+        if (lane0) mbar_arrive(bar_pfull);
       }
       // ---- finalize: O / l -> fp16 tile (q-tile, head) ----
-      mbar_wait(B.pvdone(a), pv_ph); pv_ph ^= 1;
+      mbar_wait(bar_pvdone, pv_ph); pv_ph ^= 1;
       fence_after_sync();
       const float inv = 1.f / l;
       uint8_t* tile = g.O + ((size_t)qt * (g.split_out ? 3 : 1) * g.H + h) * TILE_BYTES;
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
         uint32_t ov[32];
-        HY3D_TMEM_LD32(t_o + c * 32, ov);
+        HY3D_TMEM_LD32(to_ + c * 32, ov);
         tmem_wait_ld();
         float x[32];
 #pragma unroll

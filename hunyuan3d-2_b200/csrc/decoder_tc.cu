@@ -960,17 +960,17 @@ int launch_attn(hy3d_ctx* ctx, AttnTC a, bool fast, int fam, bool shifted = fals
       void* tm = nullptr;
       HY3D_CUDA(ctx, cudaGetSymbolAddress(&tm, hy3d_tm));
       a.timers = reinterpret_cast<unsigned long long*>(tm);
-      rc = launch_attn_kernel(ctx, k_attn_fast<4, true>, a, ATT_FAST_THREADS);
+      rc = launch_attn_kernel(ctx, k_attn_fast<2, true>, a, ATT_FAST_THREADS);
     } else {
       switch (ctx->attn_poly) {            // pairs of every 8 whose exponentials run as packed polynomials on the FMA pipe
         case 0: rc = launch_attn_kernel(ctx, k_attn_fast<0, false>, a, ATT_FAST_THREADS); break;
         case 1: rc = launch_attn_kernel(ctx, k_attn_fast<1, false>, a, ATT_FAST_THREADS); break;
-        case 2: rc = launch_attn_kernel(ctx, k_attn_fast<2, false>, a, ATT_FAST_THREADS); break;
+        case 4: rc = launch_attn_kernel(ctx, k_attn_fast<4, false>, a, ATT_FAST_THREADS); break;
         case 3: rc = launch_attn_kernel(ctx, k_attn_fast<3, false>, a, ATT_FAST_THREADS); break;
         case 5: rc = launch_attn_kernel(ctx, k_attn_fast<5, false>, a, ATT_FAST_THREADS); break;
         case 6: rc = launch_attn_kernel(ctx, k_attn_fast<6, false>, a, ATT_FAST_THREADS); break;
         case 8: rc = launch_attn_kernel(ctx, k_attn_fast<8, false>, a, ATT_FAST_THREADS); break;
-        default: rc = launch_attn_kernel(ctx, k_attn_fast<4, false>, a, ATT_FAST_THREADS); break;
+        default: rc = launch_attn_kernel(ctx, k_attn_fast<2, false>, a, ATT_FAST_THREADS); break;
       }
     }
   } else {

@@ -268,8 +268,8 @@ int hy3d_debug_retain(hy3d_ctx* ctx, int enable);
  * bounded-score attention kernel (hy3d_debug_timers), 0x10000 the CUDA-core K/V projection (results stay valid);
  * 0x100 gives every attention stream its own K/V ring even when all query tiles share one K/V set;
  * `attn_poly` = pairs of every 8 pairs of attention exponentials evaluated as packed polynomials on the FMA pipe
- * (0 none, 1 .. 6 = that many pairs, 8 = all; other values select the default, 4 = half of the exponentials).
- * Defaults (0, 4) are the product configuration. */
+ * (0 none, 1 .. 6 = that many pairs, 8 = all; other values select the default, 2 = a quarter of the exponentials).
+ * Defaults (0, 2) are the product configuration. */
 int hy3d_debug_experiment(hy3d_ctx* ctx, int bits, int attn_poly);
 /* Phase clocks accumulated by the instrumented attention kernel (experiment bit 0x40), returned and cleared:
  * per head stream a (0, 1) h_out[8a + i] = SM cycles one softmax thread of CTA 0 spent in phase i

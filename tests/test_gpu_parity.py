@@ -336,13 +336,13 @@ def test_latent_transformer_matches_oracle(tag, dev, ctx):
     vae = hy3dgeo.B200ShapeVAE(cfg, sd, device=dev)
     try:
         for bits in (0, 0x20):                       # bounded-score kernel (default for these norms), online-softmax kernel
-            ctx.debug_experiment(bits, 4)
+            ctx.debug_experiment(bits, 2)
             lat = vae(z.to(dev)).cpu()
             ctx.check_watchdog()
             d = (lat - ref).abs()
             assert lat.shape == ref.shape and float(d.max()) < 1e-3 and float(d.pow(2).mean().sqrt()) < 2e-4
     finally:
-        ctx.debug_experiment(0, 4)
+        ctx.debug_experiment(0, 2)
 
 
 # ---------------------------------------------------------------------------------- FlashVDM

@@ -20,7 +20,7 @@ ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--tag", default="")
 ap.add_argument("--no-pre", action="store_true", help="skip the transformer / K/V timings (short kernel sequence for ncu)")
 ap.add_argument("--bits", default="0", help="comma list of experiment bit sets")
-ap.add_argument("--poly", default="4", help="comma list of attn_poly values (4 = product default: half of the exponentials as polynomials)")
+ap.add_argument("--poly", default="2", help="comma list of attn_poly values (2 = product default: a quarter of the exponentials as polynomials)")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 cfg = W.FULL if args.model == "full" else W.MINI
@@ -88,4 +88,4 @@ for bits in [int(b) for b in args.bits.split(",")]:
             # MMA warp of each stream: cycles per KV tile waiting for the K tile, the S buffer, the V tile, the stored P
             res["mma_wait_clk_per_tile"] = [[round(tm[16 + 4 * a + i] / max(tm[8 * a + 7], 1)) for i in range(4)] for a in range(2)]
         print(json.dumps(res), flush=True)
-ctx.debug_experiment(0, 4)
+ctx.debug_experiment(0, 2)

@@ -20,4 +20,4 @@ for cfg, name in ((W.MINI, "mini"), (W.FULL, "full")):
         lat = vae(z.to(dev)).cpu()
         d = (lat - ref).abs()
         print(name, hex(bits), poly, "max", float(d.max()), "rms", float(d.pow(2).mean().sqrt()), "|ref|max", float(ref.abs().max()), flush=True)
-    ctx.debug_experiment(0, 4)
+    ctx.debug_experiment(0, 2)
