@@ -348,8 +348,12 @@ __global__ void __launch_bounds__(ATT_FAST_THREADS, 1) k_attn_fast(AttnTC g) {
         // while the first half's exponentials run (one TMEM round trip per tile off the stream's serial chain)
         uint32_t sv[64];
         HY3D_TMEM_LD32(ts_, sv);
-        if (g.no_pipe) { HY3D_TMEM_LD32(ts_ + 32, (sv + 32)); tmem_wait_ld(); }      // (experiment bit 0x200: both halves up front)
-        else { tmem_wait_ld(); HY3D_TMEM_LD32(ts_ + 32, (sv + 32)); }
+        if (g.no_pipe) {                                 // (experiment bit 0x200: both halves up front, S released before any exponential)
+          HY3D_TMEM_LD32(ts_ + 32, (sv + 32)); tmem_wait_ld();
+          fence_before_sync();
+          __syncwarp();
+          if (lane0) mbar_arrive(bar_sempty);
+        } else { tmem_wait_ld(); HY3D_TMEM_LD32(ts_ + 32, (sv + 32)); }
         HY3D_TICK(1)
         const int valid = ntok - j * 128 - col0;     // columns >= valid are padding tokens (last tile of a ragged count)
         bool pv_ok = j == 0, s_ok = false;
@@ -387,10 +391,12 @@ __global__ void __launch_bounds__(ATT_FAST_THREADS, 1) k_attn_fast(AttnTC g) {
           }
         };
         exp_pairs(0, 16);
-        HY3D_TMEM_WAIT_LD32((sv + 32));                // second half has landed (tied to its registers)
-        fence_before_sync();
-        __syncwarp();
-        if (lane0) mbar_arrive(bar_sempty);       // S is in registers: the next S MMA may overwrite it
+        if (!g.no_pipe) {
+          HY3D_TMEM_WAIT_LD32((sv + 32));              // second half has landed (tied to its registers)
+          fence_before_sync();
+          __syncwarp();
+          if (lane0) mbar_arrive(bar_sempty);          // S is in registers: the next S MMA may overwrite it
+        }
         if (cshift != 0.f) {
 #pragma unroll
           for (int i = 16; i < 32; ++i) {

@@ -8,8 +8,11 @@ __global__ void k(float* out, int iters, float seed) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) a[i] = seed + threadIdx.x * 1e-3f + i;
   unsigned pk = 0;
-  if (OP == 6 || OP == 7) {                       // packed f32x2: the pairs stay in 64-bit registers for the whole loop
+  if (OP >= 6) {                       // packed f32x2: the pairs stay in 64-bit registers for the whole loop
     unsigned long long v[8], sd;
+    float b[8]; int ib[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { b[i] = a[i] * 0.5f; ib[i] = threadIdx.x + i; }
     asm volatile("mov.b64 %0, {%1, %1};" : "=l"(sd) : "f"(seed));
 #pragma unroll
     for (int i = 0; i < 8; ++i) asm volatile("mov.b64 %0, {%1, %2};" : "=l"(v[i]) : "f"(a[i]), "f"(a[(i + 1) & 7]));
@@ -18,10 +21,16 @@ __global__ void k(float* out, int iters, float seed) {
       for (int i = 0; i < 8; ++i) {
         if (OP == 6) asm volatile("fma.rn.f32x2 %0, %0, %1, %1;" : "+l"(v[i]) : "l"(sd));
         if (OP == 7) asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(v[i]) : "l"(sd));
+        // mixes: does scalar FP32 / integer work issue beside the packed stream (separate pipes) or share its pipe?
+        if (OP == 8 || OP == 9 || OP == 11) asm volatile("fma.rn.f32x2 %0, %0, %1, %1;" : "+l"(v[i]) : "l"(sd));
+        if (OP == 8 || OP == 9) asm volatile("fma.rn.f32 %0, %0, %1, %1;" : "+f"(b[i]) : "f"(seed));
+        if (OP == 9) asm volatile("fma.rn.f32 %0, %0, %1, %1;" : "+f"(b[(i + 3) & 7]) : "f"(seed));
+        if (OP == 10 || OP == 11) asm volatile("mad.lo.s32 %0, %0, %1, %0;" : "+r"(ib[i]) : "r"(iters | 3));
+        if (OP == 12) asm volatile("{.reg .b32 q; shl.b32 q, %0, 3; add.s32 %0, q, %1;}" : "+r"(ib[i]) : "r"(iters));
       }
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { float x, y; asm volatile("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v[i])); a[i] = x + y; }
+    for (int i = 0; i < 8; ++i) { float x, y; asm volatile("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v[i])); a[i] = x + y + b[i] + __int_as_float(ib[i]); }
     iters = 0;
   }
   for (int it = 0; it < iters; ++it) {
@@ -59,5 +68,6 @@ void run(const char* name, int opsPerIter) {
 int main() {
   run<0>("MUFU.EX2", 1); run<1>("FADD", 1); run<2>("FFMA", 1); run<3>("F2FP", 1); run<4>("FMNMX3", 1); run<5>("EX2+2FADD", 3);
   run<6>("FFMA2(x2)", 2); run<7>("FADD2(x2)", 2);
+  run<8>("FFMA2+FFMA", 3); run<9>("FFMA2+2FFMA", 4); run<10>("IMAD", 1); run<11>("FFMA2+IMAD", 3); run<12>("SHL+ADD", 1);
   return 0;
 }
