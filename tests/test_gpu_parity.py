@@ -489,6 +489,34 @@ def test_flash_layout_minigrids_matches_oracle_order(dev, ctx):
     assert np.array_equal(sv[:G * ns].reshape(G, ns), order[:, ::stride].astype(np.int32)) and bool((sv[G * ns:] == -1).all())
 
 
+def test_flash_topk_ties_go_to_the_lower_token(dev, ctx):
+    """Radix-select top-k (k_sim_topk): latent tokens 256..511 are exact copies of tokens 0..255, so every similarity is
+    tied pairwise.  The selection must hold T distinct tokens per (mini-grid, head), and whenever the copy i + 256 is taken
+    its original i (equal key, lower index) is taken too — the count of threshold ties is exact."""
+    cfg = W.MINI
+    sd = W.synthetic_state_dict(cfg, seed=0, with_transformer=False)
+    gd = hy3dgeo.GeoDecoder(W.geo_decoder_state(sd), cfg)
+    half = torch.randn(1, 256, 1024, generator=torch.Generator().manual_seed(21))
+    lat = torch.cat([half, half], 1).to(dev)
+    c = bind(lat, gd)
+    c.prepare_kv(lat[0])
+    N0, m, T = 32, 4, 200                                   # T not a multiple of anything convenient
+    pidx, tg, sidx, soff = c.flash_layout_minigrids(N0, m, 100)
+    axes = OV.axis_tables(1.01, N0 - 1)
+    c.flash_select(sidx, (N0, N0, N0), soff, m ** 3, T, False, axes=axes)
+    G, H = m ** 3, cfg.dec_heads
+    sel = c.flash_selection(G * H * T).cpu().numpy().reshape(G, H, T)
+    c.check_watchdog()
+    assert sel.min() >= 0 and sel.max() < 512
+    for g in range(G):
+        for h in range(H):
+            row = sel[g, h]
+            chosen = set(row.tolist())
+            assert len(chosen) == T
+            assert bool((np.diff(row) > 0).all())            # emitted in ascending token order
+            assert all((t - 256) in chosen for t in chosen if t >= 256), (g, h)
+
+
 # ------------------------------------------------------------------ round 2: BASELINE configurations (goldens *_r2)
 def test_refine_odd_levels_matches_oracle(ctx):
     """Fine grids of 2n voxels per axis (the coarse level is an odd r // 2, reference vd:202-208): indices are laid out on the
