@@ -67,8 +67,10 @@ def bits_equal(a, b):
 
 # ------------------------------------------------------------------------------ marching cubes
 @pytest.mark.parametrize("shape,level", [((2, 2, 2), 0.0), ((3, 5, 33), 0.1), ((17, 9, 32), 0.0), ((9, 31, 65), -0.2),
-                                         ((20, 21, 97), 0.0)])
+                                         ((20, 21, 97), 0.0), ((6, 7, 300), 0.05), ((4, 5, 600), 0.0)])
 def test_mc_random_fields_bit_exact(ctx, shape, level):
+    """Noise fields cross the level on half of all edges: every emit work list overflows its 256 entries several times
+    (rows of 97 / 300 / 600 voxels exercise the 8-, 16- and 32-lane row layouts)."""
     rng = np.random.default_rng(sum(shape))
     vol = rng.standard_normal(shape).astype(np.float32)
     assert np.array_equal(ctx.mc_cases(torch.from_numpy(vol).cuda(), level).cpu().numpy(), OM.cube_cases(vol, level))
