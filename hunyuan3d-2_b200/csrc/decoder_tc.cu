@@ -561,7 +561,10 @@ __global__ void __launch_bounds__(128) k_embed_tc(QuerySource src, long long n, 
     for (int t = r; t < 64; t += 128) { sG[64 * 64 + t] = qs.wbar[t]; sG[64 * 64 + 64 + t] = qs.hc[t]; }
     __syncthreads();
   }
-  const long long qi = (long long)blockIdx.x * TILE_M + r;
+  // persistent over 128-row tiles: the Gram matrix is staged once per block, not once per tile
+  const int ntiles = (int)((n + TILE_M - 1) / TILE_M);
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  const long long qi = (long long)tile * TILE_M + r;
   float c[3] = {0.f, 0.f, 0.f};
   long long oi;
   if (qi < n) hy3d_query_point(src, qi, c[0], c[1], c[2], oi);
@@ -622,7 +625,7 @@ __global__ void __launch_bounds__(128) k_embed_tc(QuerySource src, long long n, 
     const int ec = kF > 0 ? kE : 3 + 6 * F;
     if (ec < 64) e[ec] = 1.0f;                                      // constant column (bias of the collapsed weight)
   }
-  uint8_t* t0 = T + (size_t)blockIdx.x * 3 * TILE_BYTES;
+  uint8_t* t0 = T + (size_t)tile * 3 * TILE_BYTES;
 #pragma unroll
   for (int c16 = 0; c16 < 8; ++c16) {
     float hi[8], lo[8];
@@ -635,6 +638,7 @@ __global__ void __launch_bounds__(128) k_embed_tc(QuerySource src, long long n, 
     store_t16_chunk(t0, r, c16, hi);
     store_t16_chunk(t0 + TILE_BYTES, r, c16, lo);
     store_t16_chunk(t0 + 2 * TILE_BYTES, r, c16, hi);
+  }
   }
 }
 
@@ -1310,8 +1314,8 @@ static int decode_tc_impl(hy3d_ctx* ctx, const QuerySource& src_in, long long n,
       HY3D_CUDA(ctx, ctx->ln_mr.reserve((size_t)chmax * sizeof(float2)));
       QStats qs{w.qs_wbar, w.qs_hc, w.qs_Gc, w.qs_scal, w.E};
       HY3D_PROF(ctx, FAM_EMBED);
-      if (w.F == 8) k_embed_tc<8><<<Pb, 128, 0, ctx->stream>>>(src, P, w.F, pi_mul, te, qs, 1e-6f, ctx->ln_mr.as<float2>());
-      else k_embed_tc<0><<<Pb, 128, 0, ctx->stream>>>(src, P, w.F, pi_mul, te, qs, 1e-6f, ctx->ln_mr.as<float2>());
+      if (w.F == 8) k_embed_tc<8><<<(Pb < ctx->num_sms * 8 ? Pb : ctx->num_sms * 8), 128, 0, ctx->stream>>>(src, P, w.F, pi_mul, te, qs, 1e-6f, ctx->ln_mr.as<float2>());
+      else k_embed_tc<0><<<(Pb < ctx->num_sms * 8 ? Pb : ctx->num_sms * 8), 128, 0, ctx->stream>>>(src, P, w.F, pi_mul, te, qs, 1e-6f, ctx->ln_mr.as<float2>());
       HY3D_LAUNCH_CHECK(ctx);
       g.Mb = Pb; g.A = te; g.B = reinterpret_cast<const uint8_t*>(w.t_cqx); g.KB = 3; g.N = W; g.Nb = W / BN; g.bias = w.bb_q; g.Tout = ta;
       g.ln_mr = ctx->ln_mr.as<float2>(); g.cs = w.cs_qx; g.ln_eps = 1e-6f;
@@ -1319,7 +1323,7 @@ static int decode_tc_impl(hy3d_ctx* ctx, const QuerySource& src_in, long long n,
       if (int rc = launch_gemm<EPI_Q>(ctx, g, FAM_GEMM_CQ)) return rc;
     } else {
       HY3D_PROF(ctx, FAM_EMBED);
-      k_embed_tc<0><<<Pb, 128, 0, ctx->stream>>>(src, P, w.F, pi_mul, te, QStats{}, 0.f, nullptr);
+      k_embed_tc<0><<<(Pb < ctx->num_sms * 8 ? Pb : ctx->num_sms * 8), 128, 0, ctx->stream>>>(src, P, w.F, pi_mul, te, QStats{}, 0.f, nullptr);
       HY3D_LAUNCH_CHECK(ctx);
       // (diagnostics: activations retained per stage) x0 = query_proj(e): fp32 residual, raw fp16 copy, row statistics
       g.Mb = Pb; g.A = te; g.B = reinterpret_cast<const uint8_t*>(w.t_qp); g.KB = 3; g.N = W; g.Nb = W / BN; g.bias = w.qp_b;
@@ -1409,7 +1413,7 @@ int hy3d_tc_sample_q(hy3d_ctx* ctx, const QuerySource& src_in, long long n, floa
     else if (src.mode == 1) src.first += p0;
     else src.index += p0;
     HY3D_PROF(ctx, FAM_SELECT);
-    k_embed_tc<0><<<Pb, 128, 0, ctx->stream>>>(src, P, w.F, pi_mul, ta, QStats{}, 0.f, nullptr);
+    k_embed_tc<0><<<(Pb < ctx->num_sms * 8 ? Pb : ctx->num_sms * 8), 128, 0, ctx->stream>>>(src, P, w.F, pi_mul, ta, QStats{}, 0.f, nullptr);
     HY3D_LAUNCH_CHECK(ctx);
     GemmTC g{};
     g.Mb = Pb; g.A = ta; g.B = reinterpret_cast<const uint8_t*>(w.t_qp); g.KB = 3; g.N = W; g.Nb = W / BN; g.bias = w.qp_b; g.Rout = x;
