@@ -38,7 +38,7 @@
 
 constexpr int ATT_SLOTS = 5;               // K / V^T ring per stream, 16 KB each
 constexpr int TM_S0 = 0, TM_P0 = 256, TM_O0 = 384;
-constexpr int ATT_THREADS = 384;           // k_attn_tc: 4 role warps + 2 x 4 softmax warps
+constexpr int ATT_THREADS = 640;           // k_attn_tc: 4 role warps + 2 x 8 softmax warps (two threads per row)
 constexpr int ATT_FAST_THREADS = 640;      // k_attn_fast: 4 role warps + 2 x 8 softmax warps
 constexpr float ATT_FAST_BOUND = 15.9f;    // exp2(15.9) = 61147 < 65504: no fp16 overflow, ever
 
@@ -82,7 +82,7 @@ struct AttnBars {                          // mbarrier addresses (shared window)
 };
 
 constexpr int ATT_TILES_BYTES = (2 + 2 * ATT_SLOTS) * TILE_BYTES;      // Q[2] + K/V ring[2][SLOTS]
-constexpr size_t ATT_SMEM = 1024 + ATT_TILES_BYTES + 512 + 2048;       // + barriers / TMEM slot + row-sum exchange (fast kernel)
+constexpr size_t ATT_SMEM = 1024 + ATT_TILES_BYTES + 512 + 2048 + 4096; // + barriers / TMEM slot + row-sum exchange + tile-maximum exchange (k_attn_tc)
 
 // Shared prologue: barriers, TMEM.  `softmax_warps` = arrivals expected on SEMPTY / PFULL per stream.
 __device__ __forceinline__ uint32_t attn_setup(uint8_t* smem, AttnBars& B, int softmax_warps, int share_kv) {
@@ -470,7 +470,12 @@ __global__ void __launch_bounds__(ATT_FAST_THREADS, 1) k_attn_fast(AttnTC g) {
 }
 
 // ------------------------------------------------------------------------------------------
-// General case: online softmax with a running maximum, one thread per query row.
+// General case: online softmax with a running maximum (decoders without q/k norm, norm gains beyond the shift range, and
+// the exact redo pass of the bounded-score kernel).  Same thread layout as k_attn_fast: two threads per query row, each
+// owning 64 of the 128 key columns of a KV tile (16 softmax warps instead of round 1's 8: twice the warps to hide the
+// TMEM / MUFU latencies).  The two halves of a row agree on the running maximum through shared memory once per tile
+// (double-buffered by tile parity, one 256-thread named barrier per stream), so they take the same lazy-rescale
+// decisions and feed ONE P tile / O accumulator.
 // ------------------------------------------------------------------------------------------
 template <int kPoly>
 __global__ void __launch_bounds__(ATT_THREADS, 1) k_attn_tc(AttnTC g) {
@@ -478,106 +483,114 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) k_attn_tc(AttnTC g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   AttnBars B;
-  const uint32_t tmem = attn_setup(smem, B, 4, g.share_kv);
+  const uint32_t tmem = attn_setup(smem, B, 8, g.share_kv);
+  float* lsum = reinterpret_cast<float*>(smem + ATT_TILES_BYTES + 512);   // [2 streams][2 halves][128 rows] row sums (finalize)
+  float* mxs = lsum + 512;                                                // [2 parities][2 streams][2 halves][128 rows] tile maxima
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nitems = attn_num_items(g), nkv = g.nkv;
 
   if (warp < 4) {
-    reg_dealloc<80>();
+    reg_dealloc<56>();
     if ((warp & 1) == 0) { if (!g.share_kv || warp == 0) attn_producer(g, B, smem, warp >> 1); }
     else attn_mma(g, B, smem, tmem, warp >> 1);
   } else {
-    reg_alloc<200>();
-    const int a = (warp - 4) >> 2;
-    const int q = warp & 3;
-    const int r = q * 32 + lane;
-    const uint32_t t_s = tmem + TM_S0 + a * 128 + ((uint32_t)(q * 32) << 16);
-    const uint32_t t_o = tmem + TM_O0 + a * 64 + ((uint32_t)(q * 32) << 16);
-    const uint32_t t_p = tmem + TM_P0 + a * 64 + ((uint32_t)(q * 32) << 16);
+    reg_alloc<104>();
+    const int a = (warp - 4) >> 3;                      // head stream
+    const int hh = ((warp - 4) >> 2) & 1;               // column half: tokens [64 hh, 64 hh + 64) of every KV tile
+    const int q = warp & 3;                             // TMEM lane quadrant
+    const int r = q * 32 + lane;                        // query row
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     uint32_t bar_sfull = B.sfull(a), bar_sempty = B.sempty(a), bar_pfull = B.pfull(a), bar_pvdone = B.pvdone(a);
-    uint32_t ts_ = t_s, tp_ = t_p, to_ = t_o, lane0 = lane == 0;       // opaque copies, see k_attn_fast
-    asm volatile("" : "+r"(bar_sfull), "+r"(bar_sempty), "+r"(bar_pfull), "+r"(bar_pvdone), "+r"(ts_), "+r"(tp_), "+r"(to_), "+r"(lane0));
+    uint32_t ts_ = tmem + TM_S0 + a * 128 + hh * 64 + lane_off, tp_ = tmem + TM_P0 + a * 64 + hh * 32 + lane_off;
+    uint32_t to_ = tmem + TM_O0 + a * 64 + hh * 32 + lane_off, lane0 = lane == 0;
+    int col0 = hh * 64;
+    float* mine = mxs + (a * 2 + hh) * 128 + r;         // + parity * 512
+    float* other = mxs + (a * 2 + (hh ^ 1)) * 128 + r;
+    asm volatile("" : "+r"(bar_sfull), "+r"(bar_sempty), "+r"(bar_pfull), "+r"(bar_pvdone), "+r"(ts_), "+r"(tp_), "+r"(to_), "+r"(lane0), "+r"(col0));   // opaque copies, see k_attn_fast
     uint32_t sfull_ph = 0, pv_ph = 0;
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
       const AttnItem wi = attn_item(g, item, a);
       const int qt = wi.qt, h = wi.h;
       const int ntok = g.group_ntok ? g.group_ntok[g.tile_group ? g.tile_group[qt] : 0] : g.ntok;
-      float m = -INFINITY, l = 0.f;
+      float m = -INFINITY;
+      uint64_t l2 = 0ull;                               // packed (even, odd column) partial row sums of this half
       for (int j = 0; j < nkv; ++j) {
         mbar_wait(bar_sfull, sfull_ph); sfull_ph ^= 1;
         fence_after_sync();
-        uint32_t sv[128];
+        uint32_t sv[64];
         HY3D_TMEM_LD32(ts_, sv); HY3D_TMEM_LD32(ts_ + 32, (sv + 32));
-        HY3D_TMEM_LD32(ts_ + 64, (sv + 64)); HY3D_TMEM_LD32(ts_ + 96, (sv + 96));
         tmem_wait_ld();
         fence_before_sync();
         __syncwarp();
         if (lane0) mbar_arrive(bar_sempty);
-        const int valid = ntok - j * 128;              // columns >= valid are padding tokens
-        if (valid < 128) {                             // only the last tile of a ragged token count
+        const int valid = ntok - j * 128 - col0;        // columns >= valid are padding tokens
+        if (valid < 64) {                               // only the last tile of a ragged token count
 #pragma unroll
-          for (int i = 0; i < 128; ++i)
-            if (i >= valid) sv[i] = 0xff800000u;       // -inf
+          for (int i = 0; i < 64; ++i)
+            if (i >= valid) sv[i] = 0xff800000u;        // -inf
         }
         float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // 4 independent max chains (3-input FMNMX)
 #pragma unroll
-        for (int i = 0; i < 128; i += 8) {
+        for (int i = 0; i < 64; i += 8) {
 #pragma unroll
           for (int u = 0; u < 4; ++u)
             mx4[u] = fmaxf(mx4[u], fmaxf(__uint_as_float(sv[i + 2 * u]), __uint_as_float(sv[i + 2 * u + 1])));
         }
-        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+        float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+        // the other half's maximum of this tile (slot = tile parity: a slot is rewritten only two barriers later)
+        mine[(j & 1) * 512] = mx;
+        asm volatile("bar.sync %0, 256;" ::"r"(1 + a) : "memory");
+        mx = fmaxf(mx, other[(j & 1) * 512]);
         bool need = false;
         float m_new = m;
         if (j == 0) { m_new = mx; }
         else if (mx > m + kLazy) { m_new = mx; need = true; }   // lazy rescale: keep the old max while p <= 2^kLazy
-        // PV(j-1) must be complete before O is rescaled or the single P buffer is overwritten.  The
-        // rescale is rare (lazy threshold): normally the wait is deferred until this tile's
-        // probabilities sit packed in registers, so the MMA has the whole exp phase to finish.
+        // PV(j-1) must be complete before O is rescaled or the single P buffer is overwritten.  The rescale is rare (lazy
+        // threshold): normally the wait is deferred until this tile's probabilities sit packed in registers.
         bool waited = (j == 0);
-        if (j > 0 && __any_sync(0xffffffffu, need)) {
+        if (j > 0 && __any_sync(0xffffffffu, need)) {    // both halves of these 32 rows see the same row maxima: same decision
           mbar_wait(bar_pvdone, pv_ph); pv_ph ^= 1; waited = true;
           fence_after_sync();
           const float sc = need ? ex2(m - m_new) : 1.f;
-          l *= sc;
-#pragma unroll 1
-          for (int c = 0; c < 2; ++c) {
-            uint32_t ov[32];
-            HY3D_TMEM_LD32(to_ + c * 32, ov);
-            tmem_wait_ld();
+          { float l0, l1; unpack_f2(l2, l0, l1); l2 = pack_f2(l0 * sc, l1 * sc); }
+          uint32_t ov[32];
+          HY3D_TMEM_LD32(to_, ov);
+          tmem_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * sc);
-            HY3D_TMEM_ST32(to_ + c * 32, ov);
-          }
+          for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * sc);
+          HY3D_TMEM_ST32(to_, ov);
           tmem_wait_st();
         }
         m = m_new;
-        float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+        const uint64_t m2 = pack_f2(m, m);
 #pragma unroll
-        for (int i = 0; i < 64; ++i) {                       // in place: sv[i] <- packed (p[2i], p[2i+1])
-          const float x0 = __uint_as_float(sv[2 * i]) - m, x1 = __uint_as_float(sv[2 * i + 1]) - m;
-          const float p0 = exp_on_fma<kPoly>(2 * i) ? exp2_poly(x0) : ex2(x0);
-          const float p1 = exp_on_fma<kPoly>(2 * i + 1) ? exp2_poly(x1) : ex2(x1);
-          sum4[i & 1] += p0; sum4[2 + (i & 1)] += p1;
+        for (int i = 0; i < 32; ++i) {                       // in place: sv[i] <- packed (p[2i], p[2i+1])
+          float x0, x1;
+          unpack_f2(sub_f2(pack_f2(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])), m2), x0, x1);
+          float p0, p1;
+          if (pair_on_fma<kPoly>(i)) exp2_poly2(fmaxf(x0, -126.f), fmaxf(x1, -126.f), p0, p1);   // (x - m can be -inf: clamp first)
+          else { p0 = ex2(x0); p1 = ex2(x1); }
+          l2 = add_f2(l2, pack_f2(p0, p1));
           sv[i] = pack_h2(p0, p1);
         }
-        l += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
         if (!waited) { mbar_wait(bar_pvdone, pv_ph); pv_ph ^= 1; }
-        HY3D_TMEM_ST32(tp_, sv); HY3D_TMEM_ST32(tp_ + 32, (sv + 32));
+        HY3D_TMEM_ST32(tp_, sv);
         tmem_wait_st();
         fence_before_sync();
         __syncwarp();
         if (lane0) mbar_arrive(bar_pfull);
       }
-      // ---- finalize: O / l -> fp16 tile (q-tile, head) ----
+      // ---- finalize: row sums of the two halves through shared memory, O / l -> fp16 tile (q-tile, head) ----
+      float* ls = lsum + a * 256;
+      { float l0, l1; unpack_f2(l2, l0, l1); ls[hh * 128 + r] = l0 + l1; }
+      asm volatile("bar.sync %0, 256;" ::"r"(1 + a) : "memory");
+      const float inv = 1.f / (ls[r] + ls[128 + r]);
       mbar_wait(bar_pvdone, pv_ph); pv_ph ^= 1;
       fence_after_sync();
-      const float inv = 1.f / l;
       uint8_t* tile = g.O + ((size_t)qt * (g.split_out ? 3 : 1) * g.H + h) * TILE_BYTES;
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
+      {
         uint32_t ov[32];
-        HY3D_TMEM_LD32(to_ + c * 32, ov);
+        HY3D_TMEM_LD32(to_, ov);
         tmem_wait_ld();
         float x[32];
 #pragma unroll
@@ -586,13 +599,14 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) k_attn_tc(AttnTC g) {
         } else if (g.split_out) {
 #pragma unroll
           for (int c16 = 0; c16 < 4; ++c16)
-            store_t16_split(tile, tile + (size_t)g.H * TILE_BYTES, tile + (size_t)2 * g.H * TILE_BYTES, r, c * 4 + c16, x + 8 * c16);
+            store_t16_split(tile, tile + (size_t)g.H * TILE_BYTES, tile + (size_t)2 * g.H * TILE_BYTES, r, hh * 4 + c16, x + 8 * c16);
         } else {
 #pragma unroll
-          for (int c16 = 0; c16 < 4; ++c16) store_t16_chunk(tile, r, c * 4 + c16, x + 8 * c16);
+          for (int c16 = 0; c16 < 4; ++c16) store_t16_chunk(tile, r, hh * 4 + c16, x + 8 * c16);
         }
       }
       fence_before_sync();
+      asm volatile("bar.sync %0, 256;" ::"r"(1 + a) : "memory");   // ls[] / mxs[] are reused by the next item
     }
   }
   fence_before_sync();
