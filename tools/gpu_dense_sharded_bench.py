@@ -40,7 +40,7 @@ def slab_path():
 
 
 def gather_path():
-    grid = P.ShardedVanillaVolumeDecoder()(vae(z), vae.geo_decoder, **kw)
+    grid = P.ShardedVanillaVolumeDecoder(keep_sharded=False)(vae(z), vae.geo_decoder, **kw)     # gathered on rank 0
     return vae.surface_extractor(grid, **kw) if rank == 0 else None
 
 
