@@ -135,3 +135,14 @@ def test_new_entry_points_are_bound():
     lib = _lib.load_library()
     for name in ("hy3d_mc_count_slab", "hy3d_mc_emit_slab", "hy3d_debug_experiment", "hy3d_debug_timers"):
         assert getattr(lib, name) is not None
+
+
+def test_tools_compile_and_are_indexed():
+    """Every measurement script under tools/ byte-compiles and is listed in tools/README.md (stale tools have hung multi-GPU
+    runs before: they are part of what a maintainer runs)."""
+    import glob, py_compile
+    tools = os.path.join(ROOT, "tools")
+    readme = open(os.path.join(tools, "README.md")).read()
+    for path in sorted(glob.glob(os.path.join(tools, "*.py"))):
+        py_compile.compile(path, doraise=True)
+        assert os.path.basename(path) in readme, f"{os.path.basename(path)} is not described in tools/README.md"
