@@ -146,3 +146,38 @@ def test_tools_compile_and_are_indexed():
     for path in sorted(glob.glob(os.path.join(tools, "*.py"))):
         py_compile.compile(path, doraise=True)
         assert os.path.basename(path) in readme, f"{os.path.basename(path)} is not described in tools/README.md"
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_plane_cuts_properties_on_cpu(seed):
+    """plane_cuts (hy3dgeo.parallel) on CPU tensors: whole planes, every entry owned once, halo entries inside the next
+    slab's first MC_HALO planes, every slab at least MC_HALO planes thick — including degenerate active sets (all actives in
+    one plane, empty leading / trailing planes, empty list)."""
+    from hy3dgeo import parallel as P
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(17, 49))
+    dens = np.zeros(n)
+    kind = seed % 3
+    if kind == 0:
+        dens[:] = rng.random(n) * 0.2
+    elif kind == 1:
+        dens[int(rng.integers(0, n))] = 0.5                       # a single populated plane
+    else:
+        lo = int(rng.integers(0, n // 2)); dens[lo: lo + n // 3] = 0.3
+    keep = rng.random((n, n * n)) < dens[:, None]
+    index = torch.from_numpy(np.flatnonzero(keep.reshape(-1)).astype(np.int32))
+    for world in (1, 2, 3, 5, 8):
+        if n < P.MC_HALO * world:
+            continue
+        planes, starts, ends = P.plane_cuts(index, n, world)
+        assert planes[0] == 0 and planes[-1] == n and starts[0] == 0 and starts[-1] == index.numel()
+        assert world == 1 or all(b - a >= P.MC_HALO for a, b in zip(planes, planes[1:]))
+        assert starts == sorted(starts) and len(starts) == world + 1 and len(ends) == world
+        for r in range(world):
+            part = index[starts[r]: starts[r + 1]].long()
+            assert part.numel() == 0 or (int(part.min()) >= planes[r] * n * n and int(part.max()) < planes[r + 1] * n * n)
+            assert ends[r] >= starts[r + 1]
+            halo = index[starts[r + 1]: ends[r]].long()
+            assert halo.numel() == 0 or int(halo.max()) < min(planes[r + 1] + P.MC_HALO, n) * n * n
+    planes, starts, ends = P.plane_cuts(index[:0], n, 2)
+    assert starts == [0, 0, 0] and planes[0] == 0 and planes[-1] == n
