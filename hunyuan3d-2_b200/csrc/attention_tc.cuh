@@ -30,10 +30,13 @@
 //    common factor cancels in O / l).  Probabilities below 2^-14 are fp16 subnormals (absolute error <= 2^-25,
 //    i.e. <= 2^-9 of the row's largest term even in the worst case of a row whose every score sits at -B; rows
 //    whose best score is >= -5 — every row of a trained or random model — lose < 2^-20 per term).  Two threads per
-//    query row (16 softmax warps) halve the serial latency of each stream; per element the instruction stream is
-//    MUFU.EX2 + FADD + half a F2FP.
-//  * k_attn_tc — online softmax with a running maximum (lazy rescale) for everything else (no q/k norm, large
-//    norm gains).  One thread per row.
+//    query row (16 softmax warps) halve the serial latency of each stream; per pair of elements the instruction
+//    stream is 2 MUFU.EX2 + FADD2 + F2FP, or the packed polynomial (3 FADD2 + 3 FFMA2 + 2 IMAD + FADD2 + F2FP) for
+//    kPoly of every 8 pairs.  Heads whose measured bound exceeds 15.9 subtract a per-head shift first (head_shift) and
+//    rows that end up far below it are flagged for an exact redo by k_attn_tc (redo_list).
+//  * k_attn_tc — online softmax with a running maximum (lazy rescale) for everything else (no q/k norm, norm gains
+//    beyond the shift range, the redo pass).  Same two-threads-per-row layout; the halves of a row exchange their
+//    tile maximum through shared memory.
 #pragma once
 
 constexpr int ATT_SLOTS = 5;               // K / V^T ring per stream, 16 KB each
