@@ -181,3 +181,24 @@ def test_plane_cuts_properties_on_cpu(seed):
             assert halo.numel() == 0 or int(halo.max()) < min(planes[r + 1] + P.MC_HALO, n) * n * n
     planes, starts, ends = P.plane_cuts(index[:0], n, 2)
     assert starts == [0, 0, 0] and planes[0] == 0 and planes[-1] == n
+
+
+def test_plain_c_host_links_against_the_cabi(tmp_path):
+    """examples/c_host_mc.c — a C99 host with no Python and no torch — compiles against include/hy3dgeo.h (strict C), links
+    against libhy3dgeo.so and runs: without a CUDA device the library refuses (exit 2, no CPU fallback); with one it extracts
+    a closed sphere mesh (exit 0)."""
+    import shutil, subprocess
+    if shutil.which("gcc") is None or not os.path.isdir("/usr/local/cuda/include"):
+        pytest.skip("gcc / CUDA headers not available")
+    so_dir = os.path.join(ROOT, "hunyuan3d-2_b200")
+    exe = str(tmp_path / "c_host_mc")
+    hdr_only = tmp_path / "hdr.c"                                  # the header alone is strict ISO C99
+    hdr_only.write_text('#include "hy3dgeo.h"\nint main(void) { return 0; }\n')
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-fsyntax-only", "-I",
+                           os.path.join(ROOT, "include"), str(hdr_only)])
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           "-I", "/usr/local/cuda/include", os.path.join(ROOT, "examples", "c_host_mc.c"),
+                           os.path.join(so_dir, "libhy3dgeo.so"), "-L", "/usr/local/cuda/lib64", "-lcudart", "-lm",
+                           f"-Wl,-rpath,{so_dir}", "-o", exe])
+    rc = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert rc.returncode == (0 if torch.cuda.is_available() else 2), rc.stdout + rc.stderr
